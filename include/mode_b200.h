@@ -1,0 +1,113 @@
+/* mode_b200.h -- C ABI of libmode_b200.so, the B200 (sm_100a) kernel library behind the
+ * MODE stereo hot path (nju-ee/MODE-2022).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller allocates every output and every workspace (reference ownership model:
+ *     models/basic/spherical_conv/sphere_conv.py:35, sphere_conv_cuda.cpp:171);
+ *   - `stream` is a cudaStream_t passed as void* (reference: kernels run on
+ *     at::cuda::getCurrentCUDAStream(), sphere_conv_cuda_kernel.cu:280);
+ *   - functions are re-entrant and keep no global state; they return 0 on success and a
+ *     negative MODE_E* code otherwise; mode_b200_last_error() gives the thread-local message
+ *     (reference: TORCH_CHECK/AT_ERROR -> RuntimeError, sphere_conv_cuda.cpp:43-124; the
+ *     reference swallows launch errors, kernel.cu:286-289 -- this library reports them);
+ *   - no function synchronises the device.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef MODE_B200_H_
+#define MODE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODE_OK 0
+#define MODE_EINVAL (-1)   /* bad shape / argument (reference: shape_check, sphere_conv_cuda.cpp:40-126) */
+#define MODE_ECUDA (-2)    /* CUDA launch / runtime error */
+#define MODE_ENOSUP (-3)   /* configuration not supported by this build */
+
+typedef uint16_t mode_bf16; /* raw bfloat16 bits */
+
+int mode_b200_version(void);
+const char* mode_b200_last_error(void);
+/* number of kernel launches issued through this library by the calling process (bench `gpu_launches`) */
+unsigned long long mode_b200_launch_count(void);
+
+/* ---- a4. concatenation cost volume ------------------------------------------------------------
+ * replaces models/mode_disparity.py:104-113 (CPU zero tensor + H2D + 2*D/4 slice copies).
+ *   cost[b,c,i,h,w]    = ref[b,c,h,w]   if w >= i else 0
+ *   cost[b,C+c,i,h,w]  = tgt[b,c,h,w-i] if w >= i else 0          i in [0, D4)
+ * f32: NCHW in, NCDHW out (bit-exact parity layout).  bf16: NHWC in, NDHWC out (the layout the
+ * tensor-core conv3d consumes).  W % 4 == 0 (f32), C % 8 == 0 (bf16). */
+int mode_cost_volume_f32(const float* ref, const float* tgt, float* cost, int B, int C, int H, int W, int D4, void* stream);
+int mode_cost_volume_bf16(const mode_bf16* ref, const mode_bf16* tgt, mode_bf16* cost, int B, int C, int H, int W, int D4, void* stream);
+
+/* ---- a6/a7. trilinear upsample + softmax + soft-argmin (+ confidence) --------------------------
+ * replaces models/mode_disparity.py:143-152 (+131-141 for the training heads), :157-183 and
+ * models/submodule.py:50-57.  cost: (B, D4, H4, W4) fp32 -> pred (B, H, W) [, conf (B, H, W) or NULL].
+ * align_corners=True scales; conf = P[r] + P[clamp(r-1)] + P[clamp(r+1)], r = rint(pred). */
+int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4, int H4, int W4, int D, int H, int W, void* stream);
+
+/* ---- a2. spherical convolution forward ----------------------------------------------------------
+ * replaces sphere_conv_forward_cuda (sphere_conv_cuda.cpp:129-210) = sphere_im2col_gpu_kernel
+ * (sphere_conv_cuda_kernel.cu:195-262) + addmm_.  stride 1, groups 1 (the only configuration MODE
+ * instantiates, models/submodule.py:128-130,161); `pos` is the (2*Kh*Kw, H, W) fp32 grid of
+ * SphereConv.gen_sphere_position.
+ * f32: x (B,C,H,W) NCHW, w (Co,C,Kh,Kw), bias (Co) or NULL, out (B,Co,H,W).
+ * Fused epilogue (both variants): y = acc*scale[co] + shift[co] (+ residual) (ReLU if relu);
+ * scale/shift/residual may be NULL. */
+int mode_sphere_conv_f32(const float* x, const float* pos, const float* w, const float* scale, const float* shift,
+                         const float* residual, float* out, int B, int C, int H, int W, int Co, int Kh, int Kw, int relu, void* stream);
+/* bf16 tensor-core variant: x (B,H,W,C) NHWC bf16, w_packed from mode_sphere_conv_pack_weights,
+ * out (B,H,W,Co) bf16.  C in {64,128}, Co = 128, 3x3. */
+int mode_sphere_conv_bf16(const mode_bf16* x, const float* pos, const mode_bf16* w_packed, const float* scale, const float* shift,
+                          const mode_bf16* residual, mode_bf16* out, int B, int C, int H, int W, int Co, int relu, void* stream);
+int mode_sphere_conv_pack_weights(const float* w /*Co,C,3,3*/, mode_bf16* w_packed, int C, int Co, void* stream);
+
+/* ---- a5. 3-D regularisation convolutions --------------------------------------------------------
+ * replace nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d(eval) + residual + ReLU
+ * (models/submodule.py:20-22, models/mode_disparity.py:11-46,66-80,115-129).  k=3, pad=1.
+ *   mode 0: conv stride 1;  mode 1: conv stride 2;  mode 2: transposed conv stride 2, output_padding 1
+ * epilogue: y = acc*scale[co] + shift[co] (+ residual) (ReLU); NULLs skip a term.
+ * f32: NCDHW, w in the PyTorch layout ((Co,Ci,3,3,3); transposed: (Ci,Co,3,3,3)).  Di/Hi/Wi are INPUT dims. */
+int mode_conv3d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* out,
+                    int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu, void* stream);
+/* bf16 tensor-core (tcgen05) variant: NDHWC bf16 activations, weights pre-packed per tap.
+ * out_f32 != NULL writes fp32 (B,Do,Ho,Wo,CoReal) instead of bf16 (used by the 32->1 classifier). */
+int mode_conv3d_pack_weights(const float* w, mode_bf16* w_packed, int Ci, int Co, int CoPad, int mode, void* stream);
+int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, const float* scale, const float* shift, const mode_bf16* residual,
+                     const float* residual_f32, mode_bf16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu,
+                     void* stream);
+size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode);
+
+/* ---- layout helpers (NCHW fp32 <-> NHWC bf16), used at the cuDNN / custom-kernel seams ----------- */
+int mode_nchw_f32_to_nhwc_bf16(const float* x, mode_bf16* y, int B, int C, int HW, void* stream);
+int mode_nhwc_bf16_to_nchw_f32(const mode_bf16* x, float* y, int B, int C, int HW, void* stream);
+
+/* ---- a8. disparity -> depth ----------------------------------------------------------------------
+ * replaces disp2depth's triangulation, save_output_disparity_stage.py:118-133.
+ * phi_l: (W) fp32 table generated on the host exactly as :118-122.  disp/depth: (B,H,W) fp32. */
+int mode_disp_to_depth(const float* disp, const float* phi_l, float* depth, int B, int H, int W, float baseline, void* stream);
+
+/* ---- a9/a11. constant-grid bilinear resampling ---------------------------------------------------
+ * replaces F.grid_sample(mode='bilinear', align_corners=True, padding_mode='border') in
+ * utils/geometry.py:38,88.  src (N,C,Hs,Ws), grid (Ho,Wo,2) shared by all N, out (N,C,Ho,Wo). */
+int mode_grid_sample_border(const float* src, const float* grid, float* out, int N, int C, int Hs, int Ws, int Ho, int Wo, void* stream);
+
+/* ---- a10. z-buffer forward warp with confidence ---------------------------------------------------
+ * replaces depthViewTransWithConf + __iterPixels_with_conf, utils/geometry.py:94-156 (fp64 geometry,
+ * fp32 buffers, strict `<`, row-major order semantics reproduced deterministically).
+ * tables: sin_phi/cos_phi (W) and sin_theta/cos_theta (H) fp32, host-generated as geometry.py:108-124.
+ * Rt_host: 12 doubles on the HOST: R row-major (9) then t (3).
+ * workspace: 3*H*W uint32 per map (keys), caller-allocated; depth/conf in, view2/conf2 out, all (B,H,W). */
+int mode_depth_view_trans(const float* depth, const float* conf, const float* sin_phi, const float* cos_phi, const float* sin_theta,
+                          const float* cos_theta, const double* Rt_host, uint32_t* workspace, float* view2, float* conf2, int B, int H,
+                          int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODE_B200_H_ */
