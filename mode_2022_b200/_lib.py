@@ -1,0 +1,71 @@
+"""ctypes binding of libmode_b200.so (C ABI declared in include/mode_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails, a RuntimeError is raised.
+ctypes releases the GIL for the duration of each call (reference: GIL held, sphere_conv_cuda.cpp has no
+gil_scoped_release), so per-GPU Python threads can drive separate streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libmode_b200.so')
+
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+
+# name -> argtypes; every function returns int status (see include/mode_b200.h)
+SIGNATURES = {
+    'mode_cost_volume_f32': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'mode_cost_volume_bf16': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'mode_disp_regress': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_sphere_conv_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_sphere_conv_bf16': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _vp],
+    'mode_conv3d_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_conv3d_pack_weights': [_vp, _vp, _i, _i, _i, _i, _vp],
+    'mode_conv3d_bf16': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_nchw_f32_to_nhwc_bf16': [_vp, _vp, _i, _i, _i, _vp],
+    'mode_nhwc_bf16_to_nchw_f32': [_vp, _vp, _i, _i, _i, _vp],
+    'mode_disp_to_depth': [_vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
+}
+OTHER_SYMBOLS = ['mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
+
+PENDING = {'mode_sphere_conv_bf16', 'mode_sphere_conv_pack_weights', 'mode_conv3d_pack_weights', 'mode_conv3d_bf16', 'mode_conv3d_packed_weight_elems'}  # TODO remove
+_lib = None
+
+
+def load() -> C.CDLL:
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(f'{LIB_PATH} is not built: run `python -m mode_2022_b200.build` (there is no fallback path)')
+  lib = C.CDLL(LIB_PATH)
+  for name, argtypes in SIGNATURES.items():
+    if name in PENDING:
+      continue
+    fn = getattr(lib, name)
+    fn.argtypes = argtypes
+    fn.restype = _i
+  lib.mode_b200_version.restype = _i
+  lib.mode_b200_last_error.restype = C.c_char_p
+  lib.mode_b200_launch_count.restype = C.c_ulonglong
+  if 'mode_conv3d_packed_weight_elems' not in PENDING:
+    lib.mode_conv3d_packed_weight_elems.argtypes = [_i, _i, _i]
+    lib.mode_conv3d_packed_weight_elems.restype = C.c_size_t
+  _lib = lib
+  return lib
+
+
+def call(name: str, *args) -> None:
+  lib = load()
+  rc = getattr(lib, name)(*args)
+  if rc != 0:
+    raise RuntimeError(f'{name} failed ({rc}): {lib.mode_b200_last_error().decode()}')
+
+
+def launch_count() -> int:
+  return int(load().mode_b200_launch_count())

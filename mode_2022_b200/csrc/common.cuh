@@ -1,0 +1,72 @@
+// common.cuh -- shared host/device helpers for libmode_b200 (sm_100a only).
+#pragma once
+#include <algorithm>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mode_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmode_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace mode {
+
+// thread-local error message + process-wide launch counter (defined in api.cu)
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define MODE_CHECK_ARG(cond, ...)                \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::mode::set_error(__VA_ARGS__);            \
+      return MODE_EINVAL;                        \
+    }                                            \
+  } while (0)
+
+#define MODE_CHECK_LAUNCH(name)                                                      \
+  do {                                                                               \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess) {                                                        \
+      ::mode::set_error("%s: CUDA error: %s", name, cudaGetErrorString(e__));        \
+      return MODE_ECUDA;                                                             \
+    }                                                                                \
+    ::mode::count_launch();                                                          \
+  } while (0)
+
+#define MODE_CHECK_CUDA(expr, name)                                                  \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      ::mode::set_error("%s: CUDA error: %s", name, cudaGetErrorString(e__));        \
+      return MODE_ECUDA;                                                             \
+    }                                                                                \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// streaming 128-bit accesses: data touched once should not pollute L1
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_na_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace mode

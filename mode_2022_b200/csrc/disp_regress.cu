@@ -1,0 +1,94 @@
+// disp_regress.cu -- fused trilinear-upsample (align_corners) + softmax over D + soft-argmin (+ confidence).
+//
+// Reference: models/mode_disparity.py:143-152 (F.upsample trilinear -> softmax -> disparityregression,
+// models/submodule.py:50-57) and :157-183 (confidence = P[r] + P[r-1] + P[r+1], border clamp).
+// The reference materialises two (B,D,H,W) fp32 volumes (403 MB each at 1024x512/D=192); this kernel reads the
+// 1/4-resolution logits (6.3 MB, L2 resident) and writes only the two (B,H,W) maps.
+//
+// Arithmetic follows ATen's upsample_trilinear3d: src = scale*dst with scale=(in-1)/(out-1) in fp32,
+// i0=(int)src, i1=i0+(i0<in-1), l1=src-i0, l0=1-l1, value = ld0*(lh0*(lw0*a+lw1*b)+lh1*(lw0*c+lw1*d)) + ld1*(...).
+// The inner (h,w) bilinear is depth independent, so it is evaluated once per 1/4-res depth plane (D/4 values,
+// kept in shared memory as t[d4][thread]) and the d-lerp + exp runs over the D fine planes from there.
+// One thread per output pixel; consecutive threads = consecutive w (coalesced output, ~8 distinct low-res
+// columns per warp so logit loads are L1 broadcasts).
+#include "common.cuh"
+using namespace mode;
+
+constexpr int kRegThreads = 256;
+
+__global__ void __launch_bounds__(kRegThreads) disp_regress_kernel(const float* __restrict__ cost, float* __restrict__ pred,
+                                                                   float* __restrict__ conf, int D4, int H4, int W4, int D, int H, int W,
+                                                                   float sd, float sh, float sw) {
+  extern __shared__ float t_s[];  // [D4][kRegThreads]
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * kRegThreads + threadIdx.x;
+  const bool active = pix < H * W;
+  const int p = active ? pix : H * W - 1;
+  const int h = p / W, w = p - h * W;
+  const float hs = sh * h, ws = sw * w;
+  const int h0 = (int)hs, w0 = (int)ws;
+  const int h1 = h0 + (h0 < H4 - 1), w1 = w0 + (w0 < W4 - 1);
+  const float lh1 = hs - h0, lw1 = ws - w0;
+  const float lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+  const float* cb = cost + (size_t)b * D4 * H4 * W4;
+  const int o00 = h0 * W4 + w0, o01 = h0 * W4 + w1, o10 = h1 * W4 + w0, o11 = h1 * W4 + w1;
+  float* t = t_s + threadIdx.x;
+  float m = -INFINITY;
+#pragma unroll 4
+  for (int d4 = 0; d4 < D4; ++d4) {
+    const float* cp = cb + (size_t)d4 * H4 * W4;
+    float v = lh0 * (lw0 * __ldg(cp + o00) + lw1 * __ldg(cp + o01)) + lh1 * (lw0 * __ldg(cp + o10) + lw1 * __ldg(cp + o11));
+    t[d4 * kRegThreads] = v;
+    m = fmaxf(m, v);
+  }
+  float sum = 0.f, wsum = 0.f;
+#pragma unroll 4
+  for (int d = 0; d < D; ++d) {
+    const float ds = sd * d;
+    const int d0 = (int)ds;
+    const int d1 = d0 + (d0 < D4 - 1);
+    const float l1 = ds - d0, l0 = 1.f - l1;
+    const float x = l0 * t[d0 * kRegThreads] + l1 * t[d1 * kRegThreads];
+    const float e = __expf(x - m);
+    sum += e;
+    wsum = fmaf(e, (float)d, wsum);
+  }
+  const float pr = wsum / sum;
+  if (!active) return;
+  pred[(size_t)b * H * W + pix] = pr;
+  if (conf != nullptr) {
+    const int r = (int)rintf(pr);  // torch.round: half-to-even (mode_disparity.py:159)
+    const float inv = 1.f / sum;
+    float c = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // order of the reference's three grid_samples: r, r-1, r+1
+      int d = r + (k == 0 ? 0 : (k == 1 ? -1 : 1));
+      d = min(max(d, 0), D - 1);
+      const float ds = sd * d;
+      const int d0 = (int)ds;
+      const int d1 = d0 + (d0 < D4 - 1);
+      const float l1 = ds - d0, l0 = 1.f - l1;
+      const float x = l0 * t[d0 * kRegThreads] + l1 * t[d1 * kRegThreads];
+      c += __expf(x - m) * inv;
+    }
+    conf[(size_t)b * H * W + pix] = c;
+  }
+}
+
+extern "C" int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4, int H4, int W4, int D, int H, int W,
+                                 void* stream) {
+  MODE_CHECK_ARG(cost && pred, "disp_regress: null pointer");
+  MODE_CHECK_ARG(B > 0 && D4 > 0 && H4 > 0 && W4 > 0 && D > 1 && H > 1 && W > 1, "disp_regress: bad shape");
+  MODE_CHECK_ARG(D4 <= 128, "disp_regress: D/4 = %d > 128 not supported", D4);
+  const float sd = (float)(D4 - 1) / (float)(D - 1), sh = (float)(H4 - 1) / (float)(H - 1), sw = (float)(W4 - 1) / (float)(W - 1);
+  const size_t smem = (size_t)D4 * kRegThreads * sizeof(float);
+  static thread_local int attr_set_for = 0;
+  if (smem > 48 * 1024 && attr_set_for < (int)smem) {
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(disp_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "disp_regress");
+    attr_set_for = (int)smem;
+  }
+  dim3 grid(ceil_div((long long)H * W, kRegThreads), B);
+  disp_regress_kernel<<<grid, kRegThreads, smem, (cudaStream_t)stream>>>(cost, pred, conf, D4, H4, W4, D, H, W, sd, sh, sw);
+  MODE_CHECK_LAUNCH("disp_regress");
+  return MODE_OK;
+}

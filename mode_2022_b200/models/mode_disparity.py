@@ -1,0 +1,125 @@
+"""ModeDisparity -- drop-in for the reference models/mode_disparity.py (same constructor, forward signature,
+output shapes and state-dict keys), executing the stereo hot path on libmode_b200 kernels:
+
+  feature extraction   regular 2-D layers: cuDNN; layer4: spherical conv kernel (a2)
+  cost volume          mode_cost_volume_*                                   (a4, reference :104-113)
+  3-D regularisation   mode_conv3d_* with BN/residual/ReLU fused            (a5, reference :11-46,:115-129)
+  regression + conf    mode_disp_regress                                    (a6/a7, reference :143-183)
+
+`precision='fp32'` is the parity mode (NCHW/NCDHW fp32 everywhere, CUDA-core kernels, <=1e-4 relative on the
+disparity); `precision='bf16'` is the throughput mode (NHWC/NDHWC bf16 activations, tcgen05 tensor-core
+kernels with fp32 accumulation and fp32 logits/regression).  Left and right images share the feature
+extractor, so they are run as one batch of 2B.
+
+Only inference is implemented in this round (the backward kernels are SURVEY.md §8f row 1): calling the
+module in training mode raises NotImplementedError rather than silently running something else.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .submodule import bn_affine, convbn, convbn_3d, sphere_feature_extraction
+
+
+class hourglass(nn.Module):
+  """Parameter holder with the reference's layout (mode_disparity.py:11-25); executed by ModeDisparity."""
+
+  def __init__(self, inplanes):
+    super().__init__()
+    self.conv1 = nn.Sequential(convbn_3d(inplanes, inplanes * 2, kernel_size=3, stride=2, pad=1), nn.ReLU(inplace=True))
+    self.conv2 = convbn_3d(inplanes * 2, inplanes * 2, kernel_size=3, stride=1, pad=1)
+    self.conv3 = nn.Sequential(convbn_3d(inplanes * 2, inplanes * 2, kernel_size=3, stride=2, pad=1), nn.ReLU(inplace=True))
+    self.conv4 = nn.Sequential(convbn_3d(inplanes * 2, inplanes * 2, kernel_size=3, stride=1, pad=1), nn.ReLU(inplace=True))
+    self.conv5 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes * 2, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
+                               nn.BatchNorm3d(inplanes * 2))
+    self.conv6 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False), nn.BatchNorm3d(inplanes))
+
+
+class ModeDisparity(nn.Module):
+  def __init__(self, maxdisp, conv='Sphere', in_height=1024, in_width=512, sphereType='Cassini', out_conf=False, precision=None):
+    super().__init__()
+    self.maxdisp = maxdisp
+    self.out_conf = out_conf
+    self.sphereType = sphereType
+    self.precision = precision or os.environ.get('MODE_B200_PRECISION', 'bf16')
+    if self.precision not in ('fp32', 'bf16'):
+      raise ValueError("precision must be 'fp32' or 'bf16'")
+    if conv == 'Regular':
+      from .psm_features import feature_extraction
+      self.feature_extraction = feature_extraction()
+    elif conv == 'Sphere':
+      self.feature_extraction = sphere_feature_extraction(in_height, in_width, sphereType)
+    else:
+      raise NotImplementedError('Convolution Type must be Regular or Sphere!')
+    self.conv_type = conv
+
+    self.dres0 = nn.Sequential(convbn_3d(64, 32, 3, 1, 1), nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True))
+    self.dres1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), convbn_3d(32, 32, 3, 1, 1))
+    self.dres2 = hourglass(32)
+    self.dres3 = hourglass(32)
+    self.dres4 = hourglass(32)
+    self.classif1 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+    self.classif2 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+    self.classif3 = nn.Sequential(convbn_3d(32, 32, 3, 1, 1), nn.ReLU(inplace=True), nn.Conv3d(32, 1, kernel_size=3, padding=1, stride=1, bias=False))
+
+    for m in self.modules():  # reference init, mode_disparity.py:82-96
+      if isinstance(m, nn.Conv2d):
+        n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+        m.weight.data.normal_(0, math.sqrt(2. / n))
+      elif isinstance(m, nn.Conv3d):
+        n = m.kernel_size[0] * m.kernel_size[1] * m.kernel_size[2] * m.out_channels
+        m.weight.data.normal_(0, math.sqrt(2. / n))
+      elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
+        m.weight.data.fill_(1)
+        m.bias.data.zero_()
+    self._plan = None
+    self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_plan())
+
+  # -------------------------------------------------------------------------------------------
+  # folded-parameter cache ("plan"): BN affines, packed bf16 weights; rebuilt after weights change
+  # -------------------------------------------------------------------------------------------
+  def invalidate_plan(self):
+    self._plan = None
+
+  def train(self, mode: bool = True):
+    self._plan = None
+    return super().train(mode)
+
+  def _apply(self, fn, *a, **k):
+    self._plan = None
+    return super()._apply(fn, *a, **k)
+
+  def load_state_dict(self, state_dict, *a, **k):
+    # accept checkpoints saved from an nn.DataParallel wrapper ('module.' prefix; reference train_disparity.py:93)
+    if state_dict and all(key.startswith('module.') for key in state_dict):
+      state_dict = {key[7:]: v for key, v in state_dict.items()}
+    return super().load_state_dict(state_dict, *a, **k)
+
+  def _build_plan(self):
+    from .plan import build_plan
+    return build_plan(self)
+
+  # -------------------------------------------------------------------------------------------
+  def forward(self, left, right):
+    if self.training:
+      raise NotImplementedError('ModeDisparity (B200): the training graph (backward kernels, SURVEY.md §8f row 1) is not built yet; '
+                                'call .eval() -- there is deliberately no PyTorch fallback')
+    if not left.is_cuda:
+      raise NotImplementedError('ModeDisparity (B200) runs on CUDA tensors only')
+    if left.shape != right.shape or left.dim() != 4 or left.shape[2] % 16 or left.shape[3] % 16:
+      raise ValueError('left/right must be (B,3,H,W) with H, W multiples of 16')
+    if self.maxdisp % 16:
+      raise ValueError('maxdisp must be a multiple of 16')
+    if self._plan is None:
+      self._plan = self._build_plan()
+    with torch.no_grad():
+      pred3, conf = self._plan.run(left, right)
+    if self.out_conf:
+      return pred3, conf
+    return pred3

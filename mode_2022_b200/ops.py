@@ -1,0 +1,255 @@
+"""torch-facing operators of the MODE hot path, backed by libmode_b200.so through ctypes.
+
+Each op is registered with torch.library (namespace `mode_b200`) with a fake (meta) implementation so it can
+be traced / graph-captured, and a CUDA implementation that forwards raw device pointers and the current
+stream to the C ABI (include/mode_b200.h).  Outputs are allocated here with the torch caching allocator and
+handed to the library (caller-allocates, as in the reference: sphere_conv.py:35).
+
+There is no CPU implementation: calling an op on CPU tensors raises NotImplementedError, like the reference
+(`Only support cuda tensor!`, sphere_conv.py:33-34).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+_lib.load()  # fail loudly at import time if the extension is missing
+
+
+def _p(t: Optional[torch.Tensor]):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+  if not t.is_cuda:
+    raise NotImplementedError(f'{name}: only CUDA tensors are supported (no CPU fallback)')
+  if t.dtype != dtype:
+    raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+  return t.contiguous()
+
+
+def _opt(t: Optional[torch.Tensor], dtype, name: str):
+  return None if t is None else _chk(t, dtype, name)
+
+
+# ------------------------------------------------------------------------------------------------
+# a4. cost volume
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op('mode_b200::cost_volume', mutates_args=())
+def cost_volume(ref: torch.Tensor, tgt: torch.Tensor, d4: int) -> torch.Tensor:
+  """fp32: (B,C,H,W) x2 -> (B,2C,D4,H,W)   [reference layout, models/mode_disparity.py:104-113]
+  bf16: (B,H,W,C) x2 -> (B,D4,H,W,2C)   [NDHWC, consumed by the tensor-core conv3d]"""
+  if ref.shape != tgt.shape or ref.dim() != 4:
+    raise ValueError('cost_volume: ref/tgt must be 4-D tensors of equal shape')
+  if ref.dtype == torch.float32:
+    ref, tgt = _chk(ref, torch.float32, 'cost_volume'), _chk(tgt, torch.float32, 'cost_volume')
+    B, Cc, H, W = ref.shape
+    out = ref.new_empty((B, 2 * Cc, d4, H, W))
+    _lib.call('mode_cost_volume_f32', _p(ref), _p(tgt), _p(out), B, Cc, H, W, d4, _stream())
+  else:
+    ref, tgt = _chk(ref, torch.bfloat16, 'cost_volume'), _chk(tgt, torch.bfloat16, 'cost_volume')
+    B, H, W, Cc = ref.shape
+    out = ref.new_empty((B, d4, H, W, 2 * Cc))
+    _lib.call('mode_cost_volume_bf16', _p(ref), _p(tgt), _p(out), B, Cc, H, W, d4, _stream())
+  return out
+
+
+@cost_volume.register_fake
+def _(ref, tgt, d4):
+  if ref.dtype == torch.float32:
+    B, Cc, H, W = ref.shape
+    return ref.new_empty((B, 2 * Cc, d4, H, W))
+  B, H, W, Cc = ref.shape
+  return ref.new_empty((B, d4, H, W, 2 * Cc))
+
+
+# ------------------------------------------------------------------------------------------------
+# a6/a7. regression + confidence
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op('mode_b200::disp_regress', mutates_args=())
+def disp_regress(cost: torch.Tensor, maxdisp: int, height: int, width: int) -> tuple[torch.Tensor, torch.Tensor]:
+  """cost (B,1,D4,H4,W4) or (B,D4,H4,W4) fp32 -> (pred, conf), both (B,1,H,W) fp32
+  (models/mode_disparity.py:143-183)."""
+  cost = _chk(cost, torch.float32, 'disp_regress')
+  if cost.dim() == 5:
+    if cost.shape[1] != 1:
+      raise ValueError('disp_regress: channel dim must be 1')
+    cost = cost[:, 0]
+  if cost.dim() != 4:
+    raise ValueError('disp_regress: expected a 4-D or 5-D cost tensor')
+  B, D4, H4, W4 = cost.shape
+  pred = cost.new_empty((B, 1, height, width))
+  conf = cost.new_empty((B, 1, height, width))
+  _lib.call('mode_disp_regress', _p(cost), _p(pred), _p(conf), B, D4, H4, W4, maxdisp, height, width, _stream())
+  return pred, conf
+
+
+@disp_regress.register_fake
+def _(cost, maxdisp, height, width):
+  B = cost.shape[0]
+  return cost.new_empty((B, 1, height, width)), cost.new_empty((B, 1, height, width))
+
+
+# ------------------------------------------------------------------------------------------------
+# a2. spherical convolution
+# ------------------------------------------------------------------------------------------------
+
+
+@torch.library.custom_op('mode_b200::sphere_conv_f32', mutates_args=())
+def sphere_conv_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                    residual: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+  """fp32 NCHW spherical conv with fused per-channel affine (+residual)(+ReLU).
+  Plain reference semantics (sphere_conv_cuda.cpp:129-210): scale=None, shift=bias, residual=None, relu=False."""
+  if x.dim() != 4:
+    raise ValueError('Expected 4D tensor as input, got {}D tensor instead.'.format(x.dim()))  # sphere_conv.py:19-20
+  if not x.is_cuda:
+    raise NotImplementedError('Only support cuda tensor!')  # sphere_conv.py:33-34
+  x = _chk(x, torch.float32, 'sphere_conv')
+  weight = _chk(weight, torch.float32, 'sphere_conv')
+  pos = _chk(pos, torch.float32, 'sphere_conv')
+  B, Cc, H, W = x.shape
+  Co, Cw, Kh, Kw = weight.shape
+  if Cw != Cc:
+    raise RuntimeError(f'Input shape and kernel channels wont match: ({Cc} vs {Cw}).')  # cpp:154-157
+  if pos.numel() != 2 * Kh * Kw * H * W:
+    raise RuntimeError(f'invalid spatial size of position, expected {2 * Kh * Kw}x{H}x{W}, got {tuple(pos.shape)}')  # cpp:93-101
+  out = x.new_empty((B, Co, H, W))
+  _lib.call('mode_sphere_conv_f32', _p(x), _p(pos), _p(weight), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
+            _p(_opt(residual, torch.float32, 'residual')), _p(out), B, Cc, H, W, Co, Kh, Kw, int(relu), _stream())
+  return out
+
+
+@sphere_conv_f32.register_fake
+def _(x, pos, weight, scale, shift, residual, relu):
+  return x.new_empty((x.shape[0], weight.shape[0], x.shape[2], x.shape[3]))
+
+
+# ------------------------------------------------------------------------------------------------
+# a5. conv3d family
+# ------------------------------------------------------------------------------------------------
+
+CONV_S1, CONV_S2, DECONV_S2 = 0, 1, 2
+
+
+def conv3d_out_dims(d, h, w, mode):
+  if mode == CONV_S1:
+    return d, h, w
+  if mode == CONV_S2:
+    return (d - 1) // 2 + 1, (h - 1) // 2 + 1, (w - 1) // 2 + 1
+  return 2 * d, 2 * h, 2 * w
+
+
+@torch.library.custom_op('mode_b200::conv3d_f32', mutates_args=())
+def conv3d_f32(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+               residual: Optional[torch.Tensor], mode: int, relu: bool) -> torch.Tensor:
+  """fp32 NCDHW 3x3x3 conv (mode 0/1) or transposed conv (mode 2) + affine + residual + ReLU
+  (models/submodule.py:20-22, models/mode_disparity.py:15-25)."""
+  x = _chk(x, torch.float32, 'conv3d')
+  weight = _chk(weight, torch.float32, 'conv3d')
+  if x.dim() != 5 or weight.dim() != 5 or tuple(weight.shape[2:]) != (3, 3, 3):
+    raise ValueError('conv3d: expected 5-D input and a 3x3x3 kernel')
+  B, Ci, D, H, W = x.shape
+  Co = weight.shape[1] if mode == DECONV_S2 else weight.shape[0]
+  if (weight.shape[0] if mode == DECONV_S2 else weight.shape[1]) != Ci:
+    raise RuntimeError('conv3d: input channels do not match the kernel')
+  Do, Ho, Wo = conv3d_out_dims(D, H, W, mode)
+  out = x.new_empty((B, Co, Do, Ho, Wo))
+  if residual is not None and residual.shape != out.shape:
+    raise RuntimeError('conv3d: residual shape mismatch')
+  _lib.call('mode_conv3d_f32', _p(x), _p(weight), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
+            _p(_opt(residual, torch.float32, 'residual')), _p(out), B, Ci, Co, D, H, W, mode, int(relu), _stream())
+  return out
+
+
+@conv3d_f32.register_fake
+def _(x, weight, scale, shift, residual, mode, relu):
+  B, Ci, D, H, W = x.shape
+  Co = weight.shape[1] if mode == DECONV_S2 else weight.shape[0]
+  return x.new_empty((B, Co, *conv3d_out_dims(D, H, W, mode)))
+
+
+# ------------------------------------------------------------------------------------------------
+# layout helpers
+# ------------------------------------------------------------------------------------------------
+
+
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+  """(B,C,*spatial) fp32 -> (B,*spatial,C) bf16."""
+  x = _chk(x, torch.float32, 'nchw_f32_to_nhwc_bf16')
+  B, Cc = x.shape[:2]
+  sp = tuple(x.shape[2:])
+  hw = 1
+  for s in sp:
+    hw *= s
+  y = torch.empty((B, *sp, Cc), dtype=torch.bfloat16, device=x.device)
+  _lib.call('mode_nchw_f32_to_nhwc_bf16', _p(x), _p(y), B, Cc, hw, _stream())
+  return y
+
+
+def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+  """(B,*spatial,C) bf16 -> (B,C,*spatial) fp32."""
+  x = _chk(x, torch.bfloat16, 'nhwc_bf16_to_nchw_f32')
+  B, Cc = x.shape[0], x.shape[-1]
+  sp = tuple(x.shape[1:-1])
+  hw = 1
+  for s in sp:
+    hw *= s
+  y = torch.empty((B, Cc, *sp), dtype=torch.float32, device=x.device)
+  _lib.call('mode_nhwc_bf16_to_nchw_f32', _p(x), _p(y), B, Cc, hw, _stream())
+  return y
+
+
+# ------------------------------------------------------------------------------------------------
+# geometry (a8-a11)
+# ------------------------------------------------------------------------------------------------
+
+
+def disp_to_depth(disp: torch.Tensor, phi_l: torch.Tensor, baseline: float) -> torch.Tensor:
+  disp = _chk(disp, torch.float32, 'disp_to_depth')
+  phi_l = _chk(phi_l, torch.float32, 'disp_to_depth')
+  H, W = disp.shape[-2:]
+  if phi_l.numel() != W:
+    raise ValueError('disp_to_depth: phi_l must have W entries')
+  out = torch.empty_like(disp)
+  _lib.call('mode_disp_to_depth', _p(disp), _p(phi_l), _p(out), disp.numel() // (H * W), H, W, C.c_float(baseline), _stream())
+  return out
+
+
+def grid_sample_border(src: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+  """src (N,C,Hs,Ws) fp32, grid (Ho,Wo,2) fp32 shared by the batch -> (N,C,Ho,Wo)."""
+  src = _chk(src, torch.float32, 'grid_sample_border')
+  grid = _chk(grid, torch.float32, 'grid_sample_border')
+  if src.dim() != 4 or grid.dim() != 3 or grid.shape[-1] != 2:
+    raise ValueError('grid_sample_border: src must be (N,C,Hs,Ws) and grid (Ho,Wo,2)')
+  N, Cc, Hs, Ws = src.shape
+  Ho, Wo = grid.shape[:2]
+  out = src.new_empty((N, Cc, Ho, Wo))
+  _lib.call('mode_grid_sample_border', _p(src), _p(grid), _p(out), N, Cc, Hs, Ws, Ho, Wo, _stream())
+  return out
+
+
+def depth_view_trans(depth: torch.Tensor, conf: torch.Tensor, sin_phi, cos_phi, sin_theta, cos_theta, Rt) -> tuple[torch.Tensor, torch.Tensor]:
+  """depth/conf (B,H,W) fp32; tables fp32 on device; Rt: 12 python floats (R row-major, then t)."""
+  depth = _chk(depth, torch.float32, 'depth_view_trans')
+  conf = _chk(conf, torch.float32, 'depth_view_trans')
+  if depth.shape != conf.shape or depth.dim() != 3:
+    raise ValueError('depth_view_trans: depth/conf must be (B,H,W) tensors of equal shape')
+  B, H, W = depth.shape
+  ws = torch.empty((3, B, H, W), dtype=torch.int32, device=depth.device)
+  v2, c2 = torch.empty_like(depth), torch.empty_like(conf)
+  rt = (C.c_double * 12)(*[float(v) for v in Rt])
+  _lib.call('mode_depth_view_trans', _p(depth), _p(conf), _p(sin_phi), _p(cos_phi), _p(sin_theta), _p(cos_theta), rt, _p(ws), _p(v2), _p(c2), B, H, W,
+            _stream())
+  return v2, c2
