@@ -88,9 +88,10 @@ int mode_nchw_f32_to_nhwc_bf16(const float* x, mode_bf16* y, int B, int C, int H
 int mode_nhwc_bf16_to_nchw_f32(const mode_bf16* x, float* y, int B, int C, int HW, void* stream);
 
 /* ---- a8. disparity -> depth ----------------------------------------------------------------------
- * replaces disp2depth's triangulation, save_output_disparity_stage.py:118-133.
- * phi_l: (W) fp32 table generated on the host exactly as :118-122.  disp/depth: (B,H,W) fp32. */
-int mode_disp_to_depth(const float* disp, const float* phi_l, float* depth, int B, int H, int W, float baseline, void* stream);
+ * replaces disp2depth's triangulation, save_output_disparity_stage.py:118-133 (fp64 arithmetic on fp32 inputs,
+ * as the reference executes under NumPy >= 2).  phi_l: (W) fp32 table generated on the host exactly as :118-122.
+ * disp (B,H,W) fp32 -> depth (B,H,W) fp32 and/or depth64 (B,H,W) fp64 (either may be NULL). */
+int mode_disp_to_depth(const float* disp, const float* phi_l, float* depth, double* depth64, int B, int H, int W, float baseline, void* stream);
 
 /* ---- a9/a11. constant-grid bilinear resampling ---------------------------------------------------
  * replaces F.grid_sample(mode='bilinear', align_corners=True, padding_mode='border') in
@@ -102,8 +103,10 @@ int mode_grid_sample_border(const float* src, const float* grid, float* out, int
  * fp32 buffers, strict `<`, row-major order semantics reproduced deterministically).
  * tables: sin_phi/cos_phi (W) and sin_theta/cos_theta (H) fp32, host-generated as geometry.py:108-124.
  * Rt_host: 12 doubles on the HOST: R row-major (9) then t (3).
- * workspace: 3*H*W uint32 per map (keys), caller-allocated; depth/conf in, view2/conf2 out, all (B,H,W). */
-int mode_depth_view_trans(const float* depth, const float* conf, const float* sin_phi, const float* cos_phi, const float* sin_theta,
+ * workspace: 3*H*W uint32 per map (keys), caller-allocated; depth/conf in, view2/conf2 out, all (B,H,W).
+ * The source depth is read from depth64 (fp64, un-rounded output of mode_disp_to_depth) when it is not NULL,
+ * else from depth (fp32); numpy's promotion rules make the two differ in the reference as well. */
+int mode_depth_view_trans(const float* depth, const double* depth64, const float* conf, const float* sin_phi, const float* cos_phi, const float* sin_theta,
                           const float* cos_theta, const double* Rt_host, uint32_t* workspace, float* view2, float* conf2, int B, int H,
                           int W, void* stream);
 

@@ -27,9 +27,9 @@ SIGNATURES = {
     'mode_conv3d_bf16': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_nchw_f32_to_nhwc_bf16': [_vp, _vp, _i, _i, _i, _vp],
     'mode_nhwc_bf16_to_nchw_f32': [_vp, _vp, _i, _i, _i, _vp],
-    'mode_disp_to_depth': [_vp, _vp, _vp, _i, _i, _i, _f, _vp],
+    'mode_disp_to_depth': [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
+    'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
 }
 OTHER_SYMBOLS = ['mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
 

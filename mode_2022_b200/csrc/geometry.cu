@@ -8,35 +8,40 @@
 using namespace mode;
 
 // ---------------------------------------------------------------------------------------------------------
-// a8.  depth = b * sin(pi/2 - phi_r) / sin(phi_r - phi_l),  phi_r = disp*pi/W + phi_l   (all fp32, numpy order)
-//      disp == 0 -> 1000; > 1000 -> 1000; < 0 -> 0.
-// fp32 op order of the numpy expression is kept (no FMA contraction across the numpy ufunc boundaries).
+// a8.  depth = b * sin(pi/2 - phi_r) / sin(phi_r - phi_l),  phi_r = disp*pi/W + phi_l;  disp == 0 -> 1000;
+//      > 1000 -> 1000; < 0 -> 0.
+// Precision follows the reference AS IT EXECUTES under NumPy >= 2 (the container's 2.3): the masked-array
+// product `disp_not_0 * math.pi` promotes to float64 (np.ma wraps the Python scalar in a 0-d float64 array,
+// which is not a weak scalar under NEP 50), so the whole triangulation runs in fp64 on the fp32 inputs.
+// The kernel writes the fp64 result (consumed un-rounded by the forward warp, as in the reference) and its
+// fp32 rounding (what rotateCassini / the fusion loader see: torch.FloatTensor / astype(float32)).
 __global__ void disp_to_depth_kernel(const float* __restrict__ disp, const float* __restrict__ phi_l, float* __restrict__ depth,
-                                     long long n, int W, float baseline) {
-  const float pi_f = 3.14159265358979323846f;        // float32(math.pi)
-  const float half_pi_f = 1.57079632679489661923f;   // float32(math.pi / 2)
+                                     double* __restrict__ depth64, long long n, int W, float baseline) {
+  const double PI = 3.141592653589793;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = disp[i];
-    const float pl = __ldg(phi_l + (int)(i % W));
-    float out;
+    const double pl = (double)__ldg(phi_l + (int)(i % W));
+    double out;
     if (d == 0.f) {
-      out = 1000.f;
+      out = 1000.0;
     } else {
-      const float pr = __fadd_rn(__fdiv_rn(__fmul_rn(d, pi_f), (float)W), pl);
-      const float num = __fmul_rn(baseline, sinf(__fsub_rn(half_pi_f, pr)));
-      out = __fdiv_rn(num, sinf(__fsub_rn(pr, pl)));
-      if (out > 1000.f) out = 1000.f;
-      if (out < 0.f) out = 0.f;
+      const double pr = __dadd_rn(__ddiv_rn(__dmul_rn((double)d, PI), (double)W), pl);
+      const double num = __dmul_rn((double)baseline, sin(__dsub_rn(PI / 2, pr)));
+      out = __ddiv_rn(num, sin(__dsub_rn(pr, pl)));
+      if (out > 1000.0) out = 1000.0;
+      if (out < 0.0) out = 0.0;
     }
-    depth[i] = out;
+    if (depth) depth[i] = (float)out;
+    if (depth64) depth64[i] = out;
   }
 }
 
-extern "C" int mode_disp_to_depth(const float* disp, const float* phi_l, float* depth, int B, int H, int W, float baseline, void* stream) {
-  MODE_CHECK_ARG(disp && phi_l && depth && B > 0 && H > 0 && W > 0, "disp_to_depth: bad arguments");
+extern "C" int mode_disp_to_depth(const float* disp, const float* phi_l, float* depth, double* depth64, int B, int H, int W, float baseline,
+                                  void* stream) {
+  MODE_CHECK_ARG(disp && phi_l && (depth || depth64) && B > 0 && H > 0 && W > 0, "disp_to_depth: bad arguments");
   const long long n = (long long)B * H * W;
   const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)kNumSMs * 16);
-  disp_to_depth_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(disp, phi_l, depth, n, W, baseline);
+  disp_to_depth_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(disp, phi_l, depth, depth64, n, W, baseline);
   MODE_CHECK_LAUNCH("disp_to_depth");
   return MODE_OK;
 }
@@ -92,14 +97,26 @@ struct RT {
   double t[3];
 };
 
-__device__ __forceinline__ void warp_target(float r1, float sp, float cp, float st, float ct, const RT& rt, int H, int W, double& r2,
-                                            int& tgt) {
-  // fp32 back-projection exactly as numpy evaluates it (geometry.py:122-124)
-  const float x1 = __fmul_rn(r1, sp);
+// back-projection exactly as numpy evaluates geometry.py:122-124: the trig tables are fp32; the products are
+// fp32 when the depth map is fp32 and fp64 when it is fp64 (numpy promotion), left to right.
+__device__ __forceinline__ void back_project(float r1, float sp, float cp, float st, float ct, double& x1, double& y1, double& z1) {
   const float rc = __fmul_rn(r1, cp);
-  const float y1 = __fmul_rn(rc, st);
-  const float z1 = __fmul_rn(rc, ct);
-  const double a = (double)x1 - rt.t[0], b = (double)y1 - rt.t[1], c = (double)z1 - rt.t[2];
+  x1 = (double)__fmul_rn(r1, sp);
+  y1 = (double)__fmul_rn(rc, st);
+  z1 = (double)__fmul_rn(rc, ct);
+}
+__device__ __forceinline__ void back_project(double r1, float sp, float cp, float st, float ct, double& x1, double& y1, double& z1) {
+  const double rc = __dmul_rn(r1, (double)cp);
+  x1 = __dmul_rn(r1, (double)sp);
+  y1 = __dmul_rn(rc, (double)st);
+  z1 = __dmul_rn(rc, (double)ct);
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_target(T r1, float sp, float cp, float st, float ct, const RT& rt, int H, int W, double& r2, int& tgt) {
+  double x1, y1, z1;
+  back_project(r1, sp, cp, st, ct, x1, y1, z1);
+  const double a = x1 - rt.t[0], b = y1 - rt.t[1], c = z1 - rt.t[2];
   const double X = __dadd_rn(__dadd_rn(__dmul_rn(rt.r[0], a), __dmul_rn(rt.r[1], b)), __dmul_rn(rt.r[2], c));
   const double Y = __dadd_rn(__dadd_rn(__dmul_rn(rt.r[3], a), __dmul_rn(rt.r[4], b)), __dmul_rn(rt.r[5], c));
   const double Z = __dadd_rn(__dadd_rn(__dmul_rn(rt.r[6], a), __dmul_rn(rt.r[7], b)), __dmul_rn(rt.r[8], c));
@@ -124,14 +141,14 @@ __global__ void warp_init_kernel(uint32_t* ws, long long n) {
   }
 }
 
-template <int PASS>
-__global__ void warp_scatter_kernel(const float* __restrict__ depth, const float* __restrict__ sp, const float* __restrict__ cp,
+template <int PASS, typename T>
+__global__ void warp_scatter_kernel(const T* __restrict__ depth, const float* __restrict__ sp, const float* __restrict__ cp,
                                     const float* __restrict__ st, const float* __restrict__ ct, RT rt, uint32_t* ws, int H, int W,
                                     long long n) {
   const int HW = H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float r1 = depth[i];
-    if (!(r1 > 0.f)) continue;
+    const T r1 = depth[i];
+    if (!(r1 > (T)0)) continue;
     const int pix = (int)(i % HW);
     const long long base = i - pix;
     const int h = pix / W, w = pix - h * W;
@@ -170,10 +187,10 @@ __global__ void warp_resolve_kernel(const float* __restrict__ conf, const uint32
   }
 }
 
-extern "C" int mode_depth_view_trans(const float* depth, const float* conf, const float* sin_phi, const float* cos_phi,
+extern "C" int mode_depth_view_trans(const float* depth, const double* depth64, const float* conf, const float* sin_phi, const float* cos_phi,
                                      const float* sin_theta, const float* cos_theta, const double* Rt_host, uint32_t* workspace,
                                      float* view2, float* conf2, int B, int H, int W, void* stream) {
-  MODE_CHECK_ARG(depth && conf && sin_phi && cos_phi && sin_theta && cos_theta && Rt_host && workspace && view2 && conf2,
+  MODE_CHECK_ARG((depth || depth64) && conf && sin_phi && cos_phi && sin_theta && cos_theta && Rt_host && workspace && view2 && conf2,
                  "depth_view_trans: null pointer");
   MODE_CHECK_ARG(B > 0 && H > 0 && W > 0 && (long long)H * W < 2147483647LL, "depth_view_trans: bad shape");
   RT rt;
@@ -184,10 +201,17 @@ extern "C" int mode_depth_view_trans(const float* depth, const float* conf, cons
   cudaStream_t s = (cudaStream_t)stream;
   warp_init_kernel<<<blocks, 256, 0, s>>>(workspace, n);
   MODE_CHECK_LAUNCH("depth_view_trans/init");
-  warp_scatter_kernel<0><<<blocks, 256, 0, s>>>(depth, sin_phi, cos_phi, sin_theta, cos_theta, rt, workspace, H, W, n);
-  MODE_CHECK_LAUNCH("depth_view_trans/min");
-  warp_scatter_kernel<1><<<blocks, 256, 0, s>>>(depth, sin_phi, cos_phi, sin_theta, cos_theta, rt, workspace, H, W, n);
-  MODE_CHECK_LAUNCH("depth_view_trans/index");
+  if (depth64) {
+    warp_scatter_kernel<0, double><<<blocks, 256, 0, s>>>(depth64, sin_phi, cos_phi, sin_theta, cos_theta, rt, workspace, H, W, n);
+    MODE_CHECK_LAUNCH("depth_view_trans/min");
+    warp_scatter_kernel<1, double><<<blocks, 256, 0, s>>>(depth64, sin_phi, cos_phi, sin_theta, cos_theta, rt, workspace, H, W, n);
+    MODE_CHECK_LAUNCH("depth_view_trans/index");
+  } else {
+    warp_scatter_kernel<0, float><<<blocks, 256, 0, s>>>(depth, sin_phi, cos_phi, sin_theta, cos_theta, rt, workspace, H, W, n);
+    MODE_CHECK_LAUNCH("depth_view_trans/min");
+    warp_scatter_kernel<1, float><<<blocks, 256, 0, s>>>(depth, sin_phi, cos_phi, sin_theta, cos_theta, rt, workspace, H, W, n);
+    MODE_CHECK_LAUNCH("depth_view_trans/index");
+  }
   warp_resolve_kernel<<<blocks, 256, 0, s>>>(conf, workspace, view2, conf2, H * W, n);
   MODE_CHECK_LAUNCH("depth_view_trans/resolve");
   return MODE_OK;

@@ -216,15 +216,17 @@ def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 
 
-def disp_to_depth(disp: torch.Tensor, phi_l: torch.Tensor, baseline: float) -> torch.Tensor:
+def disp_to_depth(disp: torch.Tensor, phi_l: torch.Tensor, baseline: float, want_f64: bool = False):
+  """disp (...,H,W) fp32 -> depth fp32 [, depth fp64 (un-rounded, for the forward warp)]."""
   disp = _chk(disp, torch.float32, 'disp_to_depth')
   phi_l = _chk(phi_l, torch.float32, 'disp_to_depth')
   H, W = disp.shape[-2:]
   if phi_l.numel() != W:
     raise ValueError('disp_to_depth: phi_l must have W entries')
   out = torch.empty_like(disp)
-  _lib.call('mode_disp_to_depth', _p(disp), _p(phi_l), _p(out), disp.numel() // (H * W), H, W, C.c_float(baseline), _stream())
-  return out
+  out64 = torch.empty_like(disp, dtype=torch.float64) if want_f64 else None
+  _lib.call('mode_disp_to_depth', _p(disp), _p(phi_l), _p(out), _p(out64), disp.numel() // (H * W), H, W, C.c_float(baseline), _stream())
+  return (out, out64) if want_f64 else out
 
 
 def grid_sample_border(src: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
@@ -241,15 +243,18 @@ def grid_sample_border(src: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
 
 
 def depth_view_trans(depth: torch.Tensor, conf: torch.Tensor, sin_phi, cos_phi, sin_theta, cos_theta, Rt) -> tuple[torch.Tensor, torch.Tensor]:
-  """depth/conf (B,H,W) fp32; tables fp32 on device; Rt: 12 python floats (R row-major, then t)."""
-  depth = _chk(depth, torch.float32, 'depth_view_trans')
+  """depth (B,H,W) fp32 or fp64, conf (B,H,W) fp32; tables fp32 on device; Rt: 12 python floats (R row-major, then t)."""
+  if depth.dtype not in (torch.float32, torch.float64):
+    raise TypeError('depth_view_trans: depth must be fp32 or fp64')
+  depth = _chk(depth, depth.dtype, 'depth_view_trans')
   conf = _chk(conf, torch.float32, 'depth_view_trans')
   if depth.shape != conf.shape or depth.dim() != 3:
     raise ValueError('depth_view_trans: depth/conf must be (B,H,W) tensors of equal shape')
   B, H, W = depth.shape
   ws = torch.empty((3, B, H, W), dtype=torch.int32, device=depth.device)
-  v2, c2 = torch.empty_like(depth), torch.empty_like(conf)
+  v2, c2 = torch.empty_like(conf), torch.empty_like(conf)
   rt = (C.c_double * 12)(*[float(v) for v in Rt])
-  _lib.call('mode_depth_view_trans', _p(depth), _p(conf), _p(sin_phi), _p(cos_phi), _p(sin_theta), _p(cos_theta), rt, _p(ws), _p(v2), _p(c2), B, H, W,
+  d32, d64 = (depth, None) if depth.dtype == torch.float32 else (None, depth)
+  _lib.call('mode_depth_view_trans', _p(d32), _p(d64), _p(conf), _p(sin_phi), _p(cos_phi), _p(sin_theta), _p(cos_theta), rt, _p(ws), _p(v2), _p(c2), B, H, W,
             _stream())
   return v2, c2

@@ -1,0 +1,207 @@
+"""GPU parity tests: every libmode_b200 kernel (through the C ABI, via mode_2022_b200.ops) against the CPU oracle
+on the same seeded inputs, plus size-independent properties at BASELINE.json's full size."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mode_oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops():
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  from mode_2022_b200 import ops as _ops
+  return _ops
+
+
+# ---------------------------------------------------------------------------- a4 cost volume
+@pytest.mark.parametrize('shape,d4', [((1, 32, 16, 8), 4), ((2, 32, 8, 16), 16), ((1, 8, 4, 4), 1), ((1, 32, 4, 8), 12)])
+def test_cost_volume_f32_bit_exact(ops, shape, d4):
+  g = torch.Generator().manual_seed(0)
+  ref, tgt = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+  out = ops.cost_volume(ref.cuda(), tgt.cuda(), d4).cpu()
+  assert torch.equal(out, O.cost_volume(ref, tgt, d4))  # pure copy: bit-exact (d4 > W exercises all-zero planes)
+
+
+def test_cost_volume_bf16_bit_exact(ops):
+  g = torch.Generator().manual_seed(1)
+  ref, tgt = torch.randn(2, 32, 16, 8, generator=g).bfloat16(), torch.randn(2, 32, 16, 8, generator=g).bfloat16()
+  out = ops.cost_volume(ref.permute(0, 2, 3, 1).contiguous().cuda(), tgt.permute(0, 2, 3, 1).contiguous().cuda(), 4).cpu()
+  want = O.cost_volume(ref.float(), tgt.float(), 4).permute(0, 2, 3, 4, 1)  # NCDHW -> NDHWC
+  assert torch.equal(out.float(), want)
+
+
+def test_cost_volume_full_size_properties(ops):
+  """1024x512 / D=192 (C1 shape): shift structure checked without a CPU copy of the 403 MB volume."""
+  ref, tgt = torch.randn(1, 32, 256, 128, device='cuda'), torch.randn(1, 32, 256, 128, device='cuda')
+  c = ops.cost_volume(ref, tgt, 48)
+  assert c.shape == (1, 64, 48, 256, 128)
+  for i in (0, 1, 17, 47):
+    assert torch.equal(c[:, :32, i, :, i:], ref[..., i:]) and torch.equal(c[:, 32:, i, :, i:], tgt[..., :128 - i])
+    assert (c[:, :, i, :, :i] == 0).all()
+
+
+# ---------------------------------------------------------------------------- a6/a7 regression
+@pytest.mark.parametrize('d4,h4,w4', [(4, 16, 8), (8, 8, 16), (16, 32, 16), (48, 8, 4)])
+def test_disp_regress(ops, d4, h4, w4):
+  g = torch.Generator().manual_seed(d4)
+  cost = torch.randn(2, 1, d4, h4, w4, generator=g) * 4
+  D, H, W = 4 * d4, 4 * h4, 4 * w4
+  pred_o, conf_o = O.disparity_regression(cost, D, H, W, want_conf=True)
+  pred, conf = ops.disp_regress(cost.cuda(), D, H, W)
+  pred, conf = pred.cpu(), conf.cpu()
+  # fp32 disparity within 1e-4 relative (north_star) -- measured against max(|d|, 1 px)
+  assert ((pred - pred_o).abs() / pred_o.abs().clamp_min(1.0)).max().item() <= 1e-4
+  same_r = torch.round(pred) == torch.round(pred_o)
+  assert same_r.float().mean().item() > 0.999
+  assert ((conf - conf_o).abs() * same_r).max().item() <= 2e-5  # three exp/sum terms, fp32
+  assert conf.max().item() <= 2.0 + 1e-5  # border clamp can count a bin twice
+
+
+def test_disp_regress_one_hot_extremes(ops):
+  """Saturated logits pin the disparity to {0, D-1} and the confidence to 2.0 at the border (clamp double count)."""
+  cost = torch.full((1, 1, 4, 4, 4), -50.0)
+  cost[0, 0, 0, :2] = 50.0
+  cost[0, 0, 3, 2:] = 50.0
+  pred, conf = ops.disp_regress(cost.cuda(), 16, 16, 16)
+  pred_o, conf_o = O.disparity_regression(cost, 16, 16, 16, want_conf=True)
+  assert torch.allclose(pred.cpu(), pred_o, atol=1e-4) and torch.allclose(conf.cpu(), conf_o, atol=1e-5)
+  assert pred.min().item() < 1e-3 and pred.max().item() > 15 - 1e-3 and conf.max().item() > 1.99
+
+
+# ---------------------------------------------------------------------------- a2 sphere conv
+def _sphere_case(B, C, Co, h, w, st, seed):
+  g = torch.Generator().manual_seed(seed)
+  H, W = (h, w)
+  x = torch.randn(B, C, H, W, generator=g)
+  wgt = torch.randn(Co, C, 3, 3, generator=g) / math.sqrt(9 * C)
+  pos = torch.from_numpy(O.gen_sphere_position(H, W, st))
+  return x, wgt, pos
+
+
+@pytest.mark.parametrize('B,C,Co,h,w,st', [(1, 1, 1, 5, 10, 'ERP'), (2, 8, 16, 16, 8, 'Cassini'), (1, 64, 128, 32, 16, 'Cassini'), (1, 128, 128, 16, 32, 'ERP'), (1, 5, 33, 16, 8, 'Cassini')])
+def test_sphere_conv_f32_vs_oracle(ops, B, C, Co, h, w, st):
+  x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 3)
+  want = O.sphere_conv(x, pos, wgt)
+  got = ops.sphere_conv_f32(x.cuda(), pos.cuda(), wgt.cuda(), None, None, None, False).cpu()
+  assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+def test_sphere_conv_f32_fused_epilogue(ops):
+  x, wgt, pos = _sphere_case(1, 16, 32, 16, 8, 'Cassini', 4)
+  scale, shift, res = torch.rand(32) + 0.5, torch.randn(32), torch.randn(1, 32, 16, 8)
+  want = F.relu(O.sphere_conv(x, pos, wgt) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+  got = ops.sphere_conv_f32(x.cuda(), pos.cuda(), wgt.cuda(), scale.cuda(), shift.cuda(), res.cuda(), True).cpu()
+  assert (got - want).abs().max().item() <= 2e-5
+
+
+def test_sphere_conv_vs_compiled_reference_op(ops):
+  """Ground truth = the UNMODIFIED reference CUDA op compiled into oracle/_ref (sphere_conv_cuda.cpp:129-210):
+  pins both the oracle's restatement and the product kernel."""
+  from oracle import build_ref
+  ref = build_ref.load()
+  if ref is None:
+    pytest.skip('oracle/_ref/sphere_conv_cuda.so not built')
+  for (B, C, Co, h, w, st) in [(2, 64, 128, 64, 32, 'Cassini'), (1, 128, 128, 32, 64, 'ERP')]:
+    x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 5)
+    xc, wc, pc = x.cuda(), wgt.cuda(), pos.cuda()
+    out = xc.new_empty((B, Co, h, w))
+    ref.sphere_conv_forward_cuda(xc, wc, xc.new_empty(1), xc.new_empty(0), pc, out, xc.new_empty(0), 3, 3, 1, 1, 1, 1, 1, 1, 1, False)
+    torch.cuda.synchronize()
+    tol = 2e-5 * max(1.0, out.abs().max().item())
+    assert (O.sphere_conv(x, pos, wgt) - out.cpu()).abs().max().item() <= tol  # oracle restatement == reference op
+    got = ops.sphere_conv_f32(xc, pc, wc, None, None, None, False)
+    assert (got - out).abs().max().item() <= tol  # product kernel == reference op
+
+
+# ---------------------------------------------------------------------------- a5 conv3d
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('ci,co,dims', [(64, 32, (4, 8, 8)), (32, 64, (6, 10, 12)), (32, 1, (4, 8, 40)), (3, 5, (5, 7, 9))])
+def test_conv3d_f32(ops, mode, ci, co, dims):
+  g = torch.Generator().manual_seed(mode * 10 + ci)
+  x = torch.randn(2, ci, *dims, generator=g)
+  w = torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), generator=g) / math.sqrt(27 * ci)
+  scale, shift = torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g)
+  want = F.conv_transpose3d(x, w, None, 2, 1, 1) if mode == 2 else F.conv3d(x, w, None, mode + 1, 1)
+  res = torch.randn(want.shape, generator=g)
+  want = F.relu(want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1) + res)
+  got = ops.conv3d_f32(x.cuda(), w.cuda(), scale.cuda(), shift.cuda(), res.cuda(), mode, True).cpu()
+  assert got.shape == want.shape
+  assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+  plain = ops.conv3d_f32(x.cuda(), w.cuda(), None, None, None, mode, False).cpu()
+  want_plain = F.conv_transpose3d(x, w, None, 2, 1, 1) if mode == 2 else F.conv3d(x, w, None, mode + 1, 1)
+  assert (plain - want_plain).abs().max().item() <= 2e-5 * max(1.0, want_plain.abs().max().item())
+
+
+# ---------------------------------------------------------------------------- layout helpers
+def test_layout_round_trip(ops):
+  x = torch.randn(2, 37, 5, 9, device='cuda')
+  y = ops.nchw_f32_to_nhwc_bf16(x)
+  assert y.shape == (2, 5, 9, 37) and torch.equal(y, x.permute(0, 2, 3, 1).bfloat16())
+  assert torch.equal(ops.nhwc_bf16_to_nchw_f32(y), x.bfloat16().float())
+
+
+# ---------------------------------------------------------------------------- a8-a11 geometry
+def test_disp2depth_all_pairs_vs_golden(ops, gold_dir):
+  from mode_2022_b200.utils import geometry as G
+  z = np.load(os.path.join(gold_dir, 'geometry_64x32.npz'))
+  disp, conf = z['disp'], z['conf']
+  for pair in G.CAM_PAIRS:
+    d, c = G.disp2depth(torch.from_numpy(disp).cuda(), torch.from_numpy(conf).cuda(), pair)
+    d, c = d.cpu().numpy().astype(np.float32), c.cpu().numpy()
+    gd, gc = z[f'depth_{pair}'], z[f'conf_{pair}']
+    if pair in ('12', '13', '14'):  # triangulation (+ bilinear resample): fp32 rounding of an fp64 expression
+      assert np.abs(d - gd).max() <= 1e-6 * max(1.0, np.abs(gd).max()) * 8, pair
+      assert np.abs(c - gc).max() <= 1e-6, pair
+    else:  # forward warp: integer targets + z-buffer; allow a handful of rint-boundary flips from libm ulps
+      bad = (np.abs(d - gd) > 1e-4 * np.maximum(1.0, np.abs(gd))) | (np.abs(c - gc) > 1e-6)
+      assert bad.mean() <= 2e-3, (pair, bad.sum())
+
+
+def test_depth_view_trans_bit_exact_on_identical_depth(ops):
+  """Same fp64 depth in -> identical integer targets, depths and confidences out (ties included)."""
+  from mode_2022_b200.utils import geometry as G
+  rng = np.random.default_rng(3)
+  conf = rng.random((64, 32), dtype=np.float32)
+  for depth in (np.full((64, 32), 2.0), rng.random((64, 32)) * 30, np.where(rng.random((64, 32)) < 0.1, 0, rng.random((64, 32)) * 1000)):
+    for dt in (np.float64, np.float32):
+      d = depth.astype(dt)
+      for pose in [(0, -1, 0, 0.5 * math.pi, 0, 0), (0, 1, 0, 0, 0, 0), (0, -math.sqrt(2) / 2, -math.sqrt(2) / 2, 0.75 * math.pi, 0, 0)]:
+        v_o, c_o = O.depth_view_trans_with_conf(d, conf, *pose)
+        v, c = G.depthViewTransWithConf(d, conf, *pose)
+        mism = (v != v_o) | (c != c_o)
+        assert mism.mean() <= 1e-3, (dt, pose, mism.sum())
+
+
+def test_rotate_and_c2e_numpy_api(ops):
+  from mode_2022_b200.utils import geometry as G
+  rng = np.random.default_rng(5)
+  img = (rng.random((64, 32)) * 100).astype(np.float32)
+  assert np.abs(G.rotateCassini(img, 0.5 * math.pi, 0, 0) - O.rotate_cassini(img, 0.5 * math.pi, 0, 0)).max() <= 1e-4
+  assert np.abs(G.rotateCassini(img[:, :, None], 0.25 * math.pi, 0, 0)[:, :, 0] - O.rotate_cassini(img, 0.25 * math.pi, 0, 0)).max() <= 1e-4
+  erp = G.cassini2Equirec(img)
+  assert erp.shape == (32, 64) and np.abs(erp - O.cassini2equirec(img)).max() <= 1e-4
+  t = torch.from_numpy(img).cuda()[None, None]
+  assert torch.allclose(G.cassini2Equirec(t).cpu()[0], torch.from_numpy(O.cassini2equirec(img)), atol=1e-4)
+
+
+def test_disp_to_depth_round_trip_full_size(ops):
+  """Full-size property: depth -> disparity by the inverse sine rule recovers the input (1024x512)."""
+  from mode_2022_b200.utils import geometry as G
+  disp = torch.rand(1024, 512, device='cuda') * 190 + 1
+  depth = G.disp_to_depth(disp, 1.0).double()
+  w = 512
+  phi_l = torch.from_numpy(np.arange(0.5 * math.pi - (0.5 * math.pi / w), -0.5 * math.pi, -(math.pi / w))).cuda().float().double()
+  ok = (depth < 1000) & (depth > 0)
+  # depth*sin(d) = cos(phi_l + d)  =>  tan(d) = cos(phi_l) / (depth + sin(phi_l)),  d = disp*pi/W
+  d_rec = torch.atan2(torch.cos(phi_l).expand_as(depth), depth + torch.sin(phi_l)) * w / math.pi
+  assert ok.float().mean().item() > 0.9
+  assert ((d_rec - disp.double()).abs()[ok]).max().item() < 2e-2

@@ -1,0 +1,78 @@
+"""CPU: host-side logic of the product -- checkpoint-key parity, bit-exact constant grids, library exports."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mode_oracle as O
+from tests import helpers as Hh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  from mode_2022_b200 import _lib
+  hdr = open(os.path.join(ROOT, 'include', 'mode_b200.h')).read()
+  declared = set(re.findall(r'\b(mode_[a-z0-9_]+)\s*\(', hdr))
+  assert len(declared) >= 15
+  lib = ctypes.CDLL(_lib.LIB_PATH)
+  missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+  assert not missing, missing
+  assert set(_lib.SIGNATURES) | set(_lib.OTHER_SYMBOLS) == declared
+  assert _lib.load().mode_b200_version() >= 100
+
+
+def test_state_dict_keys_match_reference(gold_dir):
+  from mode_2022_b200.models import ModeDisparity, ModeFusion
+  m = ModeDisparity(192, in_height=1024, in_width=512, sphereType='Cassini', out_conf=True)
+  assert {k: list(v.shape) for k, v in m.state_dict().items()} == Hh.KEY_SHAPES
+  assert sum(p.numel() for p in m.parameters()) == 5489280
+  gold = json.load(open(os.path.join(gold_dir, 'mode_fusion_keys.json')))
+  f = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12})
+  assert {k: list(v.shape) for k, v in f.state_dict().items()} == gold
+  # DataParallel-style checkpoints ('module.' prefix) load too
+  m.load_state_dict({'module.' + k: v for k, v in m.state_dict().items()})
+
+
+def test_sphere_position_bit_exact(gold_dir):
+  from mode_2022_b200.models.sphere_conv import sphere_position_numpy
+  gold = json.load(open(os.path.join(gold_dir, 'sphere_position_sha256.json')))
+  for k, v in gold.items():
+    st, hw = k.split('_')
+    h, w = map(int, hw.split('x'))
+    assert hashlib.sha256(sphere_position_numpy(min(h, w), max(h, w), st).tobytes()).hexdigest() == v, k
+
+
+def test_sphere_conv_module_contract():
+  from mode_2022_b200.models import SphereConv
+  with pytest.raises(AssertionError):
+    SphereConv(10, 10, 'Cassini', 1, 1, 3)  # long side must be 2x short side (reference sphere_conv.py:131-133)
+  sc = SphereConv(16, 8, 'Cassini', 4, 6, 3, 1, 1, 1)
+  assert list(sc.state_dict()) == ['weight'] and sc.weight.shape == (6, 4, 3, 3)
+  with pytest.raises(NotImplementedError):
+    sc(torch.zeros(1, 4, 16, 8))  # CPU tensors are rejected like the reference (sphere_conv.py:33-34)
+  with pytest.raises(ValueError):
+    sc(torch.zeros(4, 16, 8))
+
+
+def test_geometry_host_grids_bit_exact():
+  from mode_2022_b200.utils import geometry as G
+  for (h, w) in [(64, 32), (128, 64)]:
+    for pitch in (0.5 * np.pi, 0.25 * np.pi):
+      assert np.array_equal(G._rotate_grid_host(h, w, float(pitch), 0.0, 0.0), O.rotate_cassini_grid(h, w, pitch, 0, 0))
+    assert np.array_equal(G._c2e_grid_host(h, w), O.cassini2equirec_grid(h, w))
+    th, ph = G._cassini_axes(h, w)
+    tm, pm = O._cassini_angles(h, w)
+    assert np.array_equal(th, tm[:, 0]) and np.array_equal(ph, pm[0])
+
+
+def test_training_mode_fails_loudly():
+  from mode_2022_b200.models import ModeDisparity
+  m = ModeDisparity(16, in_height=64, in_width=32)
+  with pytest.raises(NotImplementedError):
+    m(torch.zeros(1, 3, 64, 32), torch.zeros(1, 3, 64, 32))
