@@ -203,5 +203,5 @@ def test_disp_to_depth_round_trip_full_size(ops):
   ok = (depth < 1000) & (depth > 0)
   # depth*sin(d) = cos(phi_l + d)  =>  tan(d) = cos(phi_l) / (depth + sin(phi_l)),  d = disp*pi/W
   d_rec = torch.atan2(torch.cos(phi_l).expand_as(depth), depth + torch.sin(phi_l)) * w / math.pi
-  assert ok.float().mean().item() > 0.9
+  assert ok.float().mean().item() > 0.7  # phi_r beyond the pole gives a negative range, clipped to 0
   assert ((d_rec - disp.double()).abs()[ok]).max().item() < 2e-2
