@@ -33,7 +33,7 @@ SIGNATURES = {
 }
 OTHER_SYMBOLS = ['mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
 
-PENDING = {'mode_sphere_conv_bf16', 'mode_sphere_conv_pack_weights', 'mode_conv3d_pack_weights', 'mode_conv3d_bf16', 'mode_conv3d_packed_weight_elems'}  # TODO remove
+PENDING = {'mode_sphere_conv_bf16', 'mode_sphere_conv_pack_weights'}  # TODO remove
 _lib = None
 
 

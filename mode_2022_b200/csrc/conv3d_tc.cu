@@ -1,0 +1,613 @@
+// conv3d_tc.cu -- 3x3x3 conv / strided conv / transposed conv on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Reference: nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d(eval) [+ residual] [+ ReLU] in the stacked hourglass
+// (models/submodule.py:20-22, models/mode_disparity.py:11-46,66-80,115-129) -- 1013.8 GFLOP per pair, the only
+// dense contraction on the hot path.
+//
+// Formulation: implicit GEMM, M = 128 output positions (a 16(h) x 8(w) tile of one depth plane), N = NT output
+// channels, K = 27 taps x Cin.  Activations are NDHWC bf16; accumulation is fp32 in TMEM; BN affine, residual and
+// ReLU are applied in the epilogue straight out of TMEM.
+//
+// Data movement (why it is not a plain im2col GEMM): with N = 32 the MMA is shared-memory-read bound and a per-tap
+// re-fetch of A from L2 would exceed the ~42 B/clk/SM L2 budget by 2.4x, so every input byte is brought on chip
+// ONCE per tile column and reused by all 27 taps:
+//   * a CTA walks a column of tiles along depth.  Each *input* plane (with its h/w halo) is staged once in shared
+//     memory and immediately consumed by every output plane it contributes to ("plane-major" order): plane p feeds
+//     outputs p-1, p, p+1 (stride 1), so three TMEM accumulators are in flight and each stage is used exactly once.
+//   * the halo tile is stored un-swizzled as [8-channel chunk][h][w][16 B] (UMMA "interleave" K-major layout: a core
+//     matrix = 8 consecutive w positions x 16 B).  A tap shift (kh, kw) is then just a different descriptor start
+//     address -- no data is moved or duplicated for the 9 in-plane taps.
+//   * stride-2 convs de-interleave the halo by (h, w) parity while staging so that the strided rows become
+//     contiguous again; transposed convs keep 4 accumulators per output plane (one per output parity class).
+//   * all 27 x Cin x NT weights stay resident in shared memory for the CTA's lifetime.
+//
+// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quadrant = warp id), warp 4 = MMA issuer (one thread),
+// warps 5-8 = producers (cp.async with zero-fill for the padding, then fence.proxy.async + mbarrier arrive).
+// Pipelines: smem ring full/empty (producer <-> MMA), TMEM set full/empty (MMA <-> epilogue).
+#include "common.cuh"
+using namespace mode;
+
+namespace {
+
+constexpr int kEpiWarps = 4, kProdWarps = 4;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 288
+constexpr int kMaxSlots = 6;
+constexpr int kMaxSets = 4;
+constexpr int kStageCh = 32;  // channels per pipeline stage (one "K half" when Cin = 64)
+
+struct TcParams {
+  const uint16_t* x;         // (B, Di, Hi, Wi, Cin) bf16
+  const uint16_t* wpk;       // packed weights [nblk][khalf][27][4][NT][8] bf16
+  const float* scale;        // [Co] or null
+  const float* shift;        // [Co] or null
+  const uint16_t* res;       // (B, Do, Ho, Wo, Co) bf16 or null
+  const float* res_f32;      // (B, Do, Ho, Wo, CoReal) fp32 or null (classifier chain)
+  uint16_t* out;             // (B, Do, Ho, Wo, Co) bf16 (or null when out_f32)
+  float* out_f32;            // (B, Do, Ho, Wo, CoReal) fp32 or null
+  int B, Cin, Co, CoReal;
+  int Di, Hi, Wi, Do, Ho, Wo;
+  int tiles_h, tiles_w, nchunks, chunk, nblk;  // chunk: output planes per item (mode 0/1), input planes (mode 2)
+  int total_items;
+  int nslots, relu;
+};
+
+template <int MODE>
+struct Geo;
+template <>
+struct Geo<0> {  // stride 1: halo 18 x 10
+  static constexpr int HV = 18, WV = 10, NV = 180, ROW = 10, NLOAD = 180, NSETS = 4, ACCS = 1;
+};
+template <>
+struct Geo<1> {  // stride 2: halo 33 x 17 stored as 4 parity sub-planes of 17 x 9
+  static constexpr int HV = 33, WV = 17, NV = 4 * 153, ROW = 9, NLOAD = 33 * 17, NSETS = 4, ACCS = 1;
+};
+template <>
+struct Geo<2> {  // transposed stride 2: halo 17 x 9 (one extra row/col on the high side), 4 parity accumulators
+  static constexpr int HV = 17, WV = 9, NV = 153, ROW = 9, NLOAD = 153, NSETS = 3, ACCS = 4;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU box
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > (1u << 24)) {
+      printf("conv3d_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B, rows 16 B apart;
+// LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);  // descriptor version 1 (Blackwell); base_offset 0, layout_type 0 = SWIZZLE_NONE
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = NT
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct Item {
+  int nb, b, th, tw, ch;
+};
+__device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
+  Item it;
+  it.ch = item % p.nchunks;
+  item /= p.nchunks;
+  it.tw = item % p.tiles_w;
+  item /= p.tiles_w;
+  it.th = item % p.tiles_h;
+  item /= p.tiles_h;
+  it.b = item % p.B;
+  it.nb = item / p.B;
+  return it;
+}
+
+// range of input planes [p0, p1] staged for chunk `ch`, and range of output planes [o0, o1) it produces
+template <int MODE>
+__device__ __forceinline__ void chunk_ranges(const TcParams& p, int ch, int& p0, int& p1, int& o0, int& o1) {
+  if (MODE == 0) {
+    o0 = ch * p.chunk, o1 = min(o0 + p.chunk, p.Do);
+    p0 = max(o0 - 1, 0), p1 = min(o1, p.Di - 1);
+  } else if (MODE == 1) {
+    o0 = ch * p.chunk, o1 = min(o0 + p.chunk, p.Do);
+    p0 = max(2 * o0 - 1, 0), p1 = min(2 * (o1 - 1) + 1, p.Di - 1);
+  } else {
+    const int j0 = ch * p.chunk, j1 = min(j0 + p.chunk, p.Di);
+    o0 = 2 * j0, o1 = 2 * j1;
+    p0 = j0, p1 = min(j1, p.Di - 1);
+  }
+}
+// first / last input plane contributing to output plane od
+template <int MODE>
+__device__ __forceinline__ void contrib_range(const TcParams& p, int od, int& first, int& last) {
+  if (MODE == 0) {
+    first = max(od - 1, 0), last = min(od + 1, p.Di - 1);
+  } else if (MODE == 1) {
+    first = max(2 * od - 1, 0), last = min(2 * od + 1, p.Di - 1);
+  } else {
+    first = od >> 1, last = (od & 1) ? min((od >> 1) + 1, p.Di - 1) : (od >> 1);
+  }
+}
+// output plane fed by input plane pl through depth tap kd (or -1)
+template <int MODE>
+__device__ __forceinline__ int out_plane(int pl, int kd) {
+  if (MODE == 0) return pl + 1 - kd;
+  if (MODE == 1) {
+    const int n = pl + 1 - kd;
+    return (n & 1) ? -1 : (n >> 1);
+  }
+  return 2 * pl - 1 + kd;
+}
+
+template <int MODE, int NT>
+__global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p) {
+  using G = Geo<MODE>;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KH = p.Cin / kStageCh;                       // K halves (1 or 2)
+  constexpr uint32_t kSlotBytes = G::NV * kStageCh * 2;  // one stage: NV voxels x 32 ch bf16
+  constexpr uint32_t kChunkStride = G::NV * 16;          // bytes between 8-channel chunks of a stage
+  const uint32_t w_bytes = (uint32_t)KH * 27 * 4 * NT * 16;
+  constexpr int kSetCols = G::ACCS * NT;
+  constexpr int kTmemCols = (G::NSETS * kSetCols <= 32) ? 32 : (G::NSETS * kSetCols <= 64) ? 64 : (G::NSETS * kSetCols <= 128) ? 128 : (G::NSETS * kSetCols <= 256) ? 256 : 512;
+  static_assert(G::NSETS * kSetCols <= 512, "TMEM overflow");
+
+  // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
+  uint8_t* w_s = smem;
+  uint8_t* slots_s = smem + ((w_bytes + 127) & ~127u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slots_s + (size_t)p.nslots * kSlotBytes);
+  uint64_t* full_bar = bars;                           // [nslots]   producers -> MMA
+  uint64_t* empty_bar = bars + kMaxSlots;              // [nslots]   MMA (commit) -> producers
+  uint64_t* tfull_bar = bars + 2 * kMaxSlots;          // [NSETS]    MMA (commit) -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kMaxSlots + kMaxSets;  // [NSETS] epilogue -> MMA
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxSets);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nslots; ++i) {
+      mbar_init(smem_u32(full_bar + i), kProdWarps);
+      mbar_init(smem_u32(empty_bar + i), 1);
+    }
+    for (int i = 0; i < G::NSETS; ++i) {
+      mbar_init(smem_u32(tfull_bar + i), 1);
+      mbar_init(smem_u32(tempty_bar + i), kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kEpiWarps) {  // the MMA warp owns the TMEM allocation
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // Work distribution: items are nb-major (nb = output-channel block); the grid is split into nblk equal groups of
+  // CTAs so that a CTA only ever sees one nb and keeps that block's weights resident for its whole lifetime.
+  const int per_nb = p.total_items / p.nblk;
+  const int ctas_per_nb = gridDim.x / p.nblk;
+  const int nb_of_cta = blockIdx.x / ctas_per_nb;
+  const int lane_cta = blockIdx.x - nb_of_cta * ctas_per_nb;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wpk) + (size_t)nb_of_cta * (w_bytes / 16);
+    uint4* dst = reinterpret_cast<uint4*>(w_s);
+    for (uint32_t i = threadIdx.x; i < w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  fence_proxy_async();  // generic-proxy smem writes (weights) -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  if (warp >= kEpiWarps + 1) {
+    // =========================================================== PRODUCERS
+    const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;  // 0..127
+    uint32_t stage = 0;                                   // global stage counter (ring position + phase)
+    bool pending = false;
+    uint32_t pending_slot = 0;
+    for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
+      const Item it = decode_item(p, nb_of_cta * per_nb + li);
+      int p0, p1, o0, o1;
+      chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+      const int h0 = it.th * 16, w0 = it.tw * 8;
+      const int gh0 = (MODE == 0) ? h0 - 1 : (MODE == 1) ? 2 * h0 - 1 : h0;
+      const int gw0 = (MODE == 0) ? w0 - 1 : (MODE == 1) ? 2 * w0 - 1 : w0;
+      for (int pl = p0; pl <= p1; ++pl) {
+        for (int kh = 0; kh < KH; ++kh, ++stage) {
+          const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
+          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+          const uint32_t sbase = smem_u32(slots_s + (size_t)slot * kSlotBytes);
+          const uint16_t* xp = p.x + ((size_t)(it.b * p.Di + pl) * p.Hi) * p.Wi * p.Cin + kh * kStageCh;
+          for (int i = ptid; i < G::NLOAD * 4; i += kProdWarps * 32) {
+            const int kc = i & 3, v = i >> 2;
+            const int hv = v / G::WV, wv = v - hv * G::WV;
+            const int gh = gh0 + hv, gw = gw0 + wv;
+            const bool ok = gh >= 0 && gh < p.Hi && gw >= 0 && gw < p.Wi;
+            int sv;
+            if (MODE == 1)
+              sv = (((hv & 1) << 1) | (wv & 1)) * 153 + (hv >> 1) * 9 + (wv >> 1);
+            else
+              sv = v;
+            const uint16_t* src = ok ? xp + ((size_t)gh * p.Wi + gw) * p.Cin + kc * 8 : p.x;
+            cp_async16(sbase + kc * kChunkStride + sv * 16, src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (pending) {  // publish the previous stage while this one is in flight
+            cp_async_wait<1>();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(full_bar + pending_slot));
+          }
+          pending = true;
+          pending_slot = slot;
+        }
+      }
+    }
+    if (pending) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(full_bar + pending_slot));
+    }
+  } else if (warp == kEpiWarps) {
+    // =========================================================== MMA ISSUER (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(NT);
+      const uint32_t w_base = smem_u32(w_s);
+      uint32_t stage = 0, job_base = 0;  // job = output plane; set = job % NSETS
+      for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
+        const Item it = decode_item(p, nb_of_cta * per_nb + li);
+        int p0, p1, o0, o1;
+        chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+        for (int pl = p0; pl <= p1; ++pl) {
+          for (int kh = 0; kh < KH; ++kh, ++stage) {
+            const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
+            mbar_wait(smem_u32(full_bar + slot), phase);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(slots_s + (size_t)slot * kSlotBytes);
+#pragma unroll 1
+            for (int kq = 0; kq < 3; ++kq) {  // oldest output plane first
+              const int kd = (MODE == 2) ? kq : 2 - kq;
+              const int od = out_plane<MODE>(pl, kd);
+              if (od < o0 || od >= o1) continue;
+              int first, last;
+              contrib_range<MODE>(p, od, first, last);
+              const uint32_t job = job_base + (uint32_t)(od - o0);
+              const uint32_t set = job % G::NSETS;
+              if (pl == first && kh == 0) {  // first touch of this accumulator set: wait until the epilogue drained it
+                mbar_wait(smem_u32(tempty_bar + set), ((job / G::NSETS) & 1) ^ 1);
+                tc_fence_after();
+              }
+              const uint32_t d_base = tmem_base + set * kSetCols;
+              const uint32_t wk = w_base + (uint32_t)(kh * 27 + kd * 9) * (4 * NT * 16);
+              if (MODE != 2) {
+                uint32_t acc = !(pl == first && kh == 0);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  const int th_ = t / 3, tw_ = t % 3;
+                  const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_)
+                                                    : (uint32_t)((((th_ & 1) << 1) | (tw_ & 1)) * 153 + (th_ >> 1) * 9 + (tw_ >> 1));
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t ad = make_desc(a_base + ks * 2 * kChunkStride + voff * 16, kChunkStride, G::ROW * 16);
+                    const uint64_t bd = make_desc(wk + (uint32_t)(t * 4 + ks * 2) * (NT * 16), NT * 16, 128);
+                    umma_bf16(d_base, ad, bd, idesc, acc);
+                    acc = 1;
+                  }
+                }
+              } else {
+                // transposed conv: output parity class (ph, pw) <- taps kh_ in {1} (ph=0) or {2 (dh=0), 0 (dh=1)} (ph=1)
+#pragma unroll
+                for (int cls = 0; cls < 4; ++cls) {
+                  const int ph = cls >> 1, pw = cls & 1;
+                  uint32_t acc = !(pl == first && kh == 0);
+#pragma unroll
+                  for (int ih = 0; ih <= ph; ++ih) {
+#pragma unroll
+                    for (int iw = 0; iw <= pw; ++iw) {
+                      const int th_ = ph ? (ih ? 0 : 2) : 1, tw_ = pw ? (iw ? 0 : 2) : 1;
+                      const uint32_t voff = (uint32_t)(ih * 9 + iw);
+#pragma unroll
+                      for (int ks = 0; ks < 2; ++ks) {
+                        const uint64_t ad = make_desc(a_base + ks * 2 * kChunkStride + voff * 16, kChunkStride, G::ROW * 16);
+                        const uint64_t bd = make_desc(wk + (uint32_t)((th_ * 3 + tw_) * 4 + ks * 2) * (NT * 16), NT * 16, 128);
+                        umma_bf16(d_base + cls * NT, ad, bd, idesc, acc);
+                        acc = 1;
+                      }
+                    }
+                  }
+                }
+              }
+              if (pl == last && kh == KH - 1) umma_commit(smem_u32(tfull_bar + set));  // accumulator complete -> epilogue
+            }
+            umma_commit(smem_u32(empty_bar + slot));  // stage consumed -> producers may refill it
+          }
+        }
+        job_base += (uint32_t)(o1 - o0);
+      }
+    }
+  } else {
+    // =========================================================== EPILOGUE (4 warps = 128 rows)
+    const int row = warp * 32 + lane;  // TMEM lane == GEMM row == tile position
+    const int hl = row >> 3, wl = row & 7;
+    uint32_t job_base = 0;
+    for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
+      const Item it = decode_item(p, nb_of_cta * per_nb + li);
+      int p0, p1, o0, o1;
+      chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+      const int n0 = it.nb * NT;
+      for (int od = o0; od < o1; ++od) {
+        const uint32_t job = job_base + (uint32_t)(od - o0);
+        const uint32_t set = job % G::NSETS;
+        mbar_wait(smem_u32(tfull_bar + set), (job / G::NSETS) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cls = 0; cls < G::ACCS; ++cls) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + set * kSetCols + cls * NT;
+          if (NT == 32)
+            tmem_ld32(taddr, v);
+          else
+            tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          int oh, ow;
+          bool ok;
+          if (MODE == 2) {
+            const int ih = it.th * 16 + hl, iw = it.tw * 8 + wl;
+            oh = 2 * ih + (cls >> 1), ow = 2 * iw + (cls & 1);
+            ok = ih < p.Hi && iw < p.Wi;
+          } else {
+            oh = it.th * 16 + hl, ow = it.tw * 8 + wl;
+            ok = oh < p.Ho && ow < p.Wo;
+          }
+          if (ok) {
+            const size_t vox = (((size_t)it.b * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+            if (p.out_f32 != nullptr) {
+              // classifier: only the first CoReal (=1) channels are real
+#pragma unroll
+              for (int c = 0; c < NT; ++c) {
+                if (c >= p.CoReal) break;
+                float y = __uint_as_float(v[c]);
+                if (p.scale) y *= __ldg(p.scale + c);
+                if (p.shift) y += __ldg(p.shift + c);
+                if (p.res_f32) y += __ldg(p.res_f32 + vox * p.CoReal + c);
+                if (p.relu) y = fmaxf(y, 0.f);
+                p.out_f32[vox * p.CoReal + c] = y;
+              }
+            } else {
+              const uint16_t* rp = p.res ? p.res + vox * p.Co + n0 : nullptr;
+              uint16_t* op = p.out + vox * p.Co + n0;
+#pragma unroll
+              for (int q = 0; q < NT / 8; ++q) {
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[q * 8 + j]);
+                if (p.scale) {
+                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q * 8));
+                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q * 8) + 1);
+                  y[0] *= s0.x, y[1] *= s0.y, y[2] *= s0.z, y[3] *= s0.w, y[4] *= s1.x, y[5] *= s1.y, y[6] *= s1.z, y[7] *= s1.w;
+                }
+                if (p.shift) {
+                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q * 8));
+                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q * 8) + 1);
+                  y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
+                }
+                if (rp) {
+                  const uint4 r = ld_nc_v4(rp + q * 8);
+                  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    y[2 * j] += __uint_as_float(rr[j] << 16);
+                    y[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                  }
+                }
+                if (p.relu) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(y[0], y[1]), o.y = pack_bf16x2(y[2], y[3]), o.z = pack_bf16x2(y[4], y[5]), o.w = pack_bf16x2(y[6], y[7]);
+                *reinterpret_cast<uint4*>(op + q * 8) = o;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + set));
+      }
+      job_base += (uint32_t)(o1 - o0);
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// weights (Co,Ci,3,3,3) [mode 0/1] or (Ci,Co,3,3,3) [mode 2], fp32 -> [nblk][khalf][27][4][NT][8] bf16, zero padded
+__global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Ci, int Co, int NT, int nblk, int mode,
+                                long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    const int j = (int)(r % 8);
+    r /= 8;
+    const int n = (int)(r % NT);
+    r /= NT;
+    const int kc = (int)(r % 4);
+    r /= 4;
+    const int t = (int)(r % 27);
+    r /= 27;
+    const int KH = Ci / kStageCh;
+    const int kh = (int)(r % KH);
+    const int nb = (int)(r / KH);
+    const int co = nb * NT + n, ci = kh * kStageCh + kc * 8 + j;
+    float v = 0.f;
+    if (co < Co) v = (mode == 2) ? w[((size_t)ci * Co + co) * 27 + t] : w[((size_t)co * Ci + ci) * 27 + t];
+    wp[e] = float_to_bf16_bits(v);
+  }
+}
+
+int pick_nt(int Co) { return Co >= 32 ? 32 : 16; }
+
+template <int MODE, int NT>
+int launch_tc(const TcParams& p, int grid, size_t smem, cudaStream_t s) {
+  static thread_local size_t attr = 0;
+  if (smem > attr) {
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_bf16");
+    attr = smem;
+  }
+  conv3d_tc_kernel<MODE, NT><<<grid, kThreads, smem, s>>>(p);
+  MODE_CHECK_LAUNCH("conv3d_bf16");
+  return MODE_OK;
+}
+
+}  // namespace
+
+extern "C" size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode) {
+  (void)mode;
+  const int NT = pick_nt(Co);
+  const int nblk = (Co + NT - 1) / NT;
+  return (size_t)nblk * (Ci / kStageCh) * 27 * 4 * NT * 8;
+}
+
+extern "C" int mode_conv3d_pack_weights(const float* w, mode_bf16* w_packed, int Ci, int Co, int CoPad, int mode, void* stream) {
+  MODE_CHECK_ARG(w && w_packed, "conv3d_pack_weights: null pointer");
+  MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_pack_weights: Ci must be 32 or 64 (got %d)", Ci);
+  MODE_CHECK_ARG(Co >= 1 && mode >= 0 && mode <= 2, "conv3d_pack_weights: bad Co/mode");
+  (void)CoPad;
+  const int NT = pick_nt(Co);
+  const int nblk = (Co + NT - 1) / NT;
+  const long long total = (long long)mode_conv3d_packed_weight_elems(Ci, Co, mode);
+  pack_w3d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, Ci, Co, NT, nblk, mode, total);
+  MODE_CHECK_LAUNCH("conv3d_pack_weights");
+  return MODE_OK;
+}
+
+extern "C" int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, const float* scale, const float* shift, const mode_bf16* residual,
+                                const float* residual_f32, mode_bf16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode,
+                                int relu, void* stream) {
+  MODE_CHECK_ARG(x && w_packed && (out || out_f32), "conv3d_bf16: null pointer");
+  MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_bf16: Ci must be 32 or 64 (got %d)", Ci);
+  MODE_CHECK_ARG(B > 0 && Di > 0 && Hi > 0 && Wi > 0 && mode >= 0 && mode <= 2, "conv3d_bf16: bad shape/mode");
+  const int NT = pick_nt(Co);
+  MODE_CHECK_ARG(out_f32 ? (Co <= 16) : (Co % 32 == 0), "conv3d_bf16: Co=%d unsupported (bf16 out needs Co %% 32 == 0, fp32 out needs Co <= 16)", Co);
+  MODE_CHECK_ARG(!(mode == 2 && NT != 32), "conv3d_bf16: transposed conv needs Co %% 32 == 0");
+  TcParams p;
+  p.x = x, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.res_f32 = residual_f32, p.out = out, p.out_f32 = out_f32;
+  p.B = B, p.Cin = Ci, p.Co = Co, p.CoReal = Co, p.Di = Di, p.Hi = Hi, p.Wi = Wi, p.relu = relu;
+  if (mode == 0) {
+    p.Do = Di, p.Ho = Hi, p.Wo = Wi;
+  } else if (mode == 1) {
+    p.Do = (Di - 1) / 2 + 1, p.Ho = (Hi - 1) / 2 + 1, p.Wo = (Wi - 1) / 2 + 1;
+  } else {
+    p.Do = 2 * Di, p.Ho = 2 * Hi, p.Wo = 2 * Wi;
+  }
+  const int th_dim = (mode == 2) ? Hi : p.Ho, tw_dim = (mode == 2) ? Wi : p.Wo, d_dim = (mode == 2) ? Di : p.Do;
+  p.tiles_h = ceil_div(th_dim, 16), p.tiles_w = ceil_div(tw_dim, 8);
+  p.nblk = ceil_div(Co, NT);
+  // shared memory: resident weights + stage ring
+  const int KH = Ci / kStageCh;
+  const size_t w_bytes = ((size_t)KH * 27 * 4 * NT * 16 + 127) & ~(size_t)127;
+  const size_t slot_bytes = (size_t)(mode == 0 ? Geo<0>::NV : mode == 1 ? Geo<1>::NV : Geo<2>::NV) * kStageCh * 2;
+  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16;
+  const size_t budget = 227 * 1024;
+  int nslots = (int)std::min<size_t>(kMaxSlots, (budget - w_bytes - misc) / slot_bytes);
+  MODE_CHECK_ARG(nslots >= 2, "conv3d_bf16: not enough shared memory for a 2-stage pipeline");
+  p.nslots = nslots;
+  // depth chunking: choose the chunk that maximises (wave efficiency) x (halo efficiency)
+  const long long cols = (long long)B * p.tiles_h * p.tiles_w;
+  const int halo = (mode == 0) ? 2 : 1;
+  int best_chunk = d_dim;
+  double best = -1;
+  for (int c = 1; c <= d_dim; ++c) {
+    const int nch = ceil_div(d_dim, c);
+    const long long items = cols * nch;
+    const long long ctas = std::min<long long>(items, kNumSMs / p.nblk);
+    const long long rounds = (items + ctas - 1) / ctas;
+    const double wave_eff = (double)items / (double)(rounds * (kNumSMs / p.nblk));
+    const double halo_eff = (double)c / (double)(c + halo);
+    const double score = wave_eff * halo_eff;
+    if (score > best + 1e-9) best = score, best_chunk = c;
+  }
+  p.chunk = best_chunk;
+  p.nchunks = ceil_div(d_dim, p.chunk);
+  const long long per_nb = cols * p.nchunks;
+  MODE_CHECK_ARG(per_nb * p.nblk < 2147483647LL, "conv3d_bf16: too many work items");
+  p.total_items = (int)(per_nb * p.nblk);
+  const int ctas_per_nb = (int)std::min<long long>(per_nb, kNumSMs / p.nblk);
+  const int grid = ctas_per_nb * p.nblk;
+  const size_t smem = w_bytes + (size_t)nslots * slot_bytes + misc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (NT == 32) {
+    if (mode == 0) return launch_tc<0, 32>(p, grid, smem, s);
+    if (mode == 1) return launch_tc<1, 32>(p, grid, smem, s);
+    return launch_tc<2, 32>(p, grid, smem, s);
+  }
+  if (mode == 0) return launch_tc<0, 16>(p, grid, smem, s);
+  if (mode == 1) return launch_tc<1, 16>(p, grid, smem, s);
+  set_error("conv3d_bf16: unsupported configuration");
+  return MODE_ENOSUP;
+}

@@ -1,0 +1,120 @@
+"""bf16 throughput plan: NHWC / NDHWC bf16 activations, tensor-core kernels, fp32 accumulation, fp32 logits."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .plan import _PlanBase, _w
+from .submodule import bn_affine
+
+
+class _FoldedConv2d:
+  """Conv2d + eval-BN folded into (bf16 channels_last weight, bias); cuDNN-backed."""
+
+  def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+    scale, shift = bn_affine(bn)
+    w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1)
+    self.w = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    self.b = shift.to(torch.bfloat16)
+    self.stride, self.padding, self.dilation = conv.stride, conv.padding, conv.dilation
+
+  def __call__(self, x, relu):
+    y = F.conv2d(x, self.w, self.b, self.stride, self.padding, self.dilation)
+    return F.relu_(y) if relu else y
+
+
+class Bf16Plan(_PlanBase):
+  def __init__(self, model):
+    self.sphere_impl = 'bf16' if hasattr(ops, 'sphere_conv_bf16') else 'f32'
+    super().__init__(model)
+    fe = model.feature_extraction
+    if model.conv_type != 'Sphere':
+      raise NotImplementedError("precision='bf16' supports conv='Sphere' (the MODE configuration); use precision='fp32' for conv='Regular'")
+    fc = fe.firstconv
+    self.first = [_FoldedConv2d(fc[0][0], fc[0][1]), _FoldedConv2d(fc[2][0], fc[2][1]), _FoldedConv2d(fc[4][0], fc[4][1])]
+    self.regular = []
+    for layer in (fe.layer1, fe.layer2, fe.layer3):
+      blocks = []
+      for blk in layer:
+        ds = _FoldedConv2d(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+        blocks.append((_FoldedConv2d(blk.conv1[0][0], blk.conv1[0][1]), _FoldedConv2d(blk.conv2[0], blk.conv2[1]), ds))
+      self.regular.append(blocks)
+    lc = fe.lastconv
+    self.last = [_FoldedConv2d(lc[0][0], lc[0][1]), _FoldedConv2d(lc[2][0], lc[2][1]), _FoldedConv2d(lc[4][0], lc[4][1])]
+    self.l4 = []
+    for blk in fe.layer4:
+      c1, b1 = blk.conv1[0][0], blk.conv1[0][1]
+      c2, b2 = blk.conv2[0], blk.conv2[1]
+      ds = _FoldedConv2d(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+      if self.sphere_impl == 'bf16':
+        self.l4.append((c1, ops.sphere_conv_pack_weights(_w(c1)), bn_affine(b1), ops.sphere_conv_pack_weights(_w(c2)), bn_affine(b2), ds))
+      else:
+        self.l4.append((c1, _w(c1), bn_affine(b1), _w(c2), bn_affine(b2), ds))
+
+  def pack_conv3d(self, w, scale, shift, mode):
+    cout = w.shape[1] if mode == ops.DECONV_S2 else w.shape[0]
+    return (ops.conv3d_pack_weights(w, mode), cout, scale, shift, mode)
+
+  # ---- 2-D feature extractor: bf16 channels_last (physically NHWC) ------------------------------
+  def _regular_layer(self, x, blocks):
+    for c1, c2, ds in blocks:
+      out = c2(c1(x, True), False)
+      res = ds(x, False) if ds is not None else x
+      x = F.relu_(out.add_(res))
+    return x
+
+  def features(self, x):
+    x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    for c in self.first:
+      x = c(x, True)
+    x = self._regular_layer(x, self.regular[0])
+    raw = self._regular_layer(x, self.regular[1])
+    reg = self._regular_layer(raw, self.regular[2])
+    if self.sphere_impl == 'bf16':
+      y = reg.permute(0, 2, 3, 1)  # NHWC view of the channels_last tensor (zero copy)
+      if not y.is_contiguous():
+        y = y.contiguous()
+      for (c1, w1, (s1, h1), w2, (s2, h2), ds) in self.l4:
+        pos = c1.position
+        o = ops.sphere_conv_bf16(y, pos, w1, c1.out_channels, s1, h1, None, True)
+        res = ds(y.permute(0, 3, 1, 2), False).permute(0, 2, 3, 1) if ds is not None else y
+        y = ops.sphere_conv_bf16(o, pos, w2, c1.out_channels, s2, h2, res.contiguous(), True)
+      sph = y.permute(0, 3, 1, 2)
+    else:  # interim: fp32 CUDA-core sphere conv between bf16 neighbours
+      y = reg.float().contiguous()
+      for (c1, w1, (s1, h1), w2, (s2, h2), ds) in self.l4:
+        pos = c1.position
+        o = ops.sphere_conv_f32(y, pos, w1, s1, h1, None, True)
+        res = ds(y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last), False).float().contiguous() if ds is not None else y
+        y = ops.sphere_conv_f32(o, pos, w2, s2, h2, res, True)
+      sph = y.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    f = torch.cat((raw, reg, sph), 1).contiguous(memory_format=torch.channels_last)
+    f = self.last[0](f, True)
+    f = self.last[1](f, True)
+    f = self.last[2](f, True)
+    return f  # (2B, 32, H/4, W/4) bf16 channels_last
+
+  def cost_volume(self, fl, fr, d4):
+    fl, fr = fl.permute(0, 2, 3, 1), fr.permute(0, 2, 3, 1)  # NHWC views
+    return ops.cost_volume(fl.contiguous(), fr.contiguous(), d4)  # (B, D4, H4, W4, 64) bf16
+
+  def conv3d(self, x, key, relu, residual=None):
+    wp, cout, scale, shift, mode = self.p3[key]
+    return ops.conv3d_bf16(x, wp, cout, scale, shift, residual, mode, relu, False)
+
+  def logits(self, x, key, residual):
+    wp, cout, _, _, mode = self.p3[key]
+    out = ops.conv3d_bf16(x, wp, cout, None, None, residual, mode, False, True)  # (B, D4, H4, W4, 1) fp32
+    return out
+
+  def run(self, left, right, return_stages=False):
+    B, _, H, W = left.shape
+    feat = self.features(torch.cat([left, right], 0))
+    cost = self.cost_volume(feat[:B], feat[B:], self.maxdisp // 4)
+    cost1, cost2, cost3 = self.regularise(cost)
+    pred, conf = ops.disp_regress(cost3[..., 0], self.maxdisp, H, W)
+    if return_stages:
+      return pred, conf, dict(feat=feat, cost=cost, cost1=cost1[..., 0], cost2=cost2[..., 0], cost3=cost3[..., 0])
+    return pred, conf

@@ -180,6 +180,44 @@ def _(x, weight, scale, shift, residual, mode, relu):
   return x.new_empty((B, Co, *conv3d_out_dims(D, H, W, mode)))
 
 
+def conv3d_pack_weights(weight: torch.Tensor, mode: int) -> torch.Tensor:
+  """fp32 PyTorch-layout 3x3x3 weights -> per-tap bf16 tiles resident in shared memory ([nblk][khalf][27][4][NT][8])."""
+  weight = _chk(weight, torch.float32, 'conv3d_pack_weights')
+  Ci, Co = (weight.shape[0], weight.shape[1]) if mode == DECONV_S2 else (weight.shape[1], weight.shape[0])
+  n = _lib.load().mode_conv3d_packed_weight_elems(Ci, Co, mode)
+  out = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
+  _lib.call('mode_conv3d_pack_weights', _p(weight), _p(out), Ci, Co, 0, mode, _stream())
+  return out
+
+
+@torch.library.custom_op('mode_b200::conv3d_bf16', mutates_args=())
+def conv3d_bf16(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                residual: Optional[torch.Tensor], mode: int, relu: bool, out_f32: bool) -> torch.Tensor:
+  """NDHWC bf16 3x3x3 conv / strided conv / transposed conv on tcgen05 tensor cores with fused affine + residual
+  + ReLU.  x (B,D,H,W,Ci) bf16 -> (B,Do,Ho,Wo,cout) bf16; with out_f32 (cout <= 16, the 32->1 classifier) the
+  output and the residual are fp32."""
+  x = _chk(x, torch.bfloat16, 'conv3d_bf16')
+  w_packed = _chk(w_packed, torch.bfloat16, 'conv3d_bf16')
+  if x.dim() != 5:
+    raise ValueError('conv3d_bf16: expected (B,D,H,W,C) input')
+  B, D, H, W, Ci = x.shape
+  Do, Ho, Wo = conv3d_out_dims(D, H, W, mode)
+  out = torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+  if residual is not None and residual.shape != out.shape:
+    raise RuntimeError('conv3d_bf16: residual shape mismatch')
+  res_bf16 = _opt(residual, torch.bfloat16, 'residual') if not out_f32 else None
+  res_f32 = _opt(residual, torch.float32, 'residual') if out_f32 else None
+  _lib.call('mode_conv3d_bf16', _p(x), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')), _p(res_bf16),
+            _p(res_f32), _p(None if out_f32 else out), _p(out if out_f32 else None), B, Ci, cout, D, H, W, mode, int(relu), _stream())
+  return out
+
+
+@conv3d_bf16.register_fake
+def _(x, w_packed, cout, scale, shift, residual, mode, relu, out_f32):
+  B, D, H, W, Ci = x.shape
+  return torch.empty((B, *conv3d_out_dims(D, H, W, mode), cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+
+
 # ------------------------------------------------------------------------------------------------
 # layout helpers
 # ------------------------------------------------------------------------------------------------

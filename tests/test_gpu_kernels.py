@@ -205,3 +205,56 @@ def test_disp_to_depth_round_trip_full_size(ops):
   d_rec = torch.atan2(torch.cos(phi_l).expand_as(depth), depth + torch.sin(phi_l)) * w / math.pi
   assert ok.float().mean().item() > 0.7  # phi_r beyond the pole gives a negative range, clipped to 0
   assert ((d_rec - disp.double()).abs()[ok]).max().item() < 2e-2
+
+
+# ---------------------------------------------------------------------------- a5 conv3d on tensor cores (bf16)
+def _tc_case(ops, mode, ci, co, dims, B, seed, relu=True, with_res=True, with_affine=True):
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(B, ci, *dims, generator=g).bfloat16()
+  w = (torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), generator=g) / math.sqrt(27 * ci))
+  wq = w.bfloat16().float()  # the kernel multiplies bf16-rounded weights
+  scale = (torch.rand(co, generator=g) + 0.5) if with_affine else None
+  shift = torch.randn(co, generator=g) if with_affine else None
+  want = F.conv_transpose3d(x.float(), wq, None, 2, 1, 1) if mode == 2 else F.conv3d(x.float(), wq, None, mode + 1, 1)
+  res = torch.randn(want.shape, generator=g).bfloat16() if with_res else None
+  if with_affine:
+    want = want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
+  if with_res:
+    want = want + res.float()
+  if relu:
+    want = F.relu(want)
+  wp = ops.conv3d_pack_weights(w.cuda(), mode)
+  got = ops.conv3d_bf16(x.permute(0, 2, 3, 4, 1).contiguous().cuda(), wp, co, scale.cuda() if with_affine else None, shift.cuda() if with_affine else None,
+                        res.permute(0, 2, 3, 4, 1).contiguous().cuda() if with_res else None, mode, relu, False)
+  torch.cuda.synchronize()
+  got = got.float().cpu().permute(0, 4, 1, 2, 3)
+  assert got.shape == want.shape
+  err = (got - want).abs()
+  tol = 2.0**-7 * want.abs().clamp_min(1.0)  # bf16 output rounding (2^-9 rel) + fp32 accumulation-order noise
+  assert (err <= tol).all(), (mode, ci, co, dims, err.max().item(), (err / tol).max().item())
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+@pytest.mark.parametrize('ci,co', [(32, 32), (64, 32), (32, 64), (64, 64)])
+def test_conv3d_bf16_tensor_core(ops, mode, ci, co):
+  _tc_case(ops, mode, ci, co, (6, 16, 8), 1, seed=mode * 100 + ci + co)          # exactly one tile column
+  _tc_case(ops, mode, ci, co, (5, 22, 13), 2, seed=mode * 100 + ci + co + 1)     # ragged tiles, odd dims, batch 2
+
+
+def test_conv3d_bf16_plain_and_large(ops):
+  _tc_case(ops, 0, 32, 32, (12, 48, 40), 1, seed=7, relu=False, with_res=False, with_affine=False)
+  _tc_case(ops, 0, 64, 32, (16, 64, 32), 1, seed=8)
+  _tc_case(ops, 1, 32, 64, (16, 64, 32), 1, seed=9)
+  _tc_case(ops, 2, 64, 32, (8, 32, 16), 1, seed=10)
+
+
+def test_conv3d_bf16_classifier_fp32_out(ops):
+  g = torch.Generator().manual_seed(11)
+  x = torch.randn(2, 32, 6, 20, 12, generator=g).bfloat16()
+  w = torch.randn(1, 32, 3, 3, 3, generator=g) / math.sqrt(27 * 32)
+  res = torch.randn(2, 1, 6, 20, 12, generator=g)
+  want = F.conv3d(x.float(), w.bfloat16().float(), None, 1, 1) + res
+  wp = ops.conv3d_pack_weights(w.cuda(), 0)
+  got = ops.conv3d_bf16(x.permute(0, 2, 3, 4, 1).contiguous().cuda(), wp, 1, None, None, res.permute(0, 2, 3, 4, 1).contiguous().cuda(), 0, False, True)
+  assert got.dtype == torch.float32 and got.shape == (2, 6, 20, 12, 1)
+  assert (got.cpu().permute(0, 4, 1, 2, 3) - want).abs().max().item() <= 1e-4
