@@ -82,6 +82,8 @@ int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, const float*
                      const float* residual_f32, mode_bf16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu,
                      void* stream);
 size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode);
+/* profiling aid: when set (device pointer to >= 8*grid int64), every conv3d_bf16 launch records per-CTA {smid, start ns, end ns, items} */
+int mode_conv3d_set_debug_buffer(void* dev_ptr);
 
 /* ---- layout helpers (NCHW fp32 <-> NHWC bf16), used at the cuDNN / custom-kernel seams ----------- */
 int mode_nchw_f32_to_nhwc_bf16(const float* x, mode_bf16* y, int B, int C, int HW, void* stream);

@@ -31,7 +31,7 @@ SIGNATURES = {
     'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
 }
-OTHER_SYMBOLS = ['mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
+OTHER_SYMBOLS = ['mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
 
 PENDING = {'mode_sphere_conv_bf16', 'mode_sphere_conv_pack_weights'}  # TODO remove
 _lib = None

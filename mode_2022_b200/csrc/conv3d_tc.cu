@@ -32,7 +32,7 @@ namespace {
 constexpr int kEpiWarps = 4, kProdWarps = 4;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 288
 constexpr int kMaxSlots = 6;
-constexpr int kMaxSets = 4;
+constexpr int kMaxSets = 32;  // TMEM accumulator blocks (512 columns / NT) or sets (transposed conv)
 constexpr int kStageCh = 32;  // channels per pipeline stage (one "K half" when Cin = 64)
 
 struct TcParams {
@@ -49,21 +49,22 @@ struct TcParams {
   int tiles_h, tiles_w, nchunks, chunk, nblk;  // chunk: output planes per item (mode 0/1), input planes (mode 2)
   int total_items;
   int nslots, relu;
+  long long* dbg;            // optional per-CTA timing records [grid][4]: smid, t_start, t_end, n_items (profiling aid)
 };
 
 template <int MODE>
 struct Geo;
 template <>
 struct Geo<0> {  // stride 1: halo 18 x 10
-  static constexpr int HV = 18, WV = 10, NV = 180, ROW = 10, NLOAD = 180, NSETS = 4, ACCS = 1;
+  static constexpr int HV = 18, WV = 10, NV = 180, ROW = 10, NLOAD = 180, ACCS = 1;
 };
 template <>
 struct Geo<1> {  // stride 2: halo 33 x 17 stored as 4 parity sub-planes of 17 x 9
-  static constexpr int HV = 33, WV = 17, NV = 4 * 153, ROW = 9, NLOAD = 33 * 17, NSETS = 4, ACCS = 1;
+  static constexpr int HV = 33, WV = 17, NV = 4 * 153, ROW = 9, NLOAD = 33 * 17, ACCS = 1;
 };
 template <>
 struct Geo<2> {  // transposed stride 2: halo 17 x 9 (one extra row/col on the high side), 4 parity accumulators
-  static constexpr int HV = 17, WV = 9, NV = 153, ROW = 9, NLOAD = 153, NSETS = 3, ACCS = 4;
+  static constexpr int HV = 17, WV = 9, NV = 153, ROW = 9, NLOAD = 153, ACCS = 4;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -138,6 +139,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// zero 32 (or 16) consecutive TMEM columns of this warp's 32 lanes
+template <int NCOL>
+__device__ __forceinline__ void tmem_zero(uint32_t taddr) {
+  const uint32_t z = 0;
+  if (NCOL == 32) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// MMA with descriptors passed as (lo, hi) halves so that per-tap updates are single 32-bit adds
+__device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }  // version 1 at bit 46
 
 // UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B, rows 16 B apart;
 // LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
@@ -203,27 +241,39 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
   return 2 * pl - 1 + kd;
 }
 
+// Weight block order inside one (tap, k-chunk) group for the depth-stacked MMAs (mode 0/1): blocks are sorted by
+// ascending OUTPUT plane so that one MMA with N = nb*NT updates nb adjacent TMEM accumulator blocks at once.
+//   mode 0: block = 2 - kd  (kd = 2 -> oldest output plane p-1, kd = 0 -> newest p+1)
+//   mode 1: odd input planes feed kd = 2 (block 0) and kd = 0 (block 1); even planes feed kd = 1 (block 2)
+__host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
+
 template <int MODE, int NT>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p) {
   using G = Geo<MODE>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
+  long long t_start = 0;
+  if (p.dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  const int lane = threadIdx.x & 31;
   const int KH = p.Cin / kStageCh;                       // K halves (1 or 2)
   constexpr uint32_t kSlotBytes = G::NV * kStageCh * 2;  // one stage: NV voxels x 32 ch bf16
   constexpr uint32_t kChunkStride = G::NV * 16;          // bytes between 8-channel chunks of a stage
   const uint32_t w_bytes = (uint32_t)KH * 27 * 4 * NT * 16;
+  // TMEM: mode 0/1 use a ring of R = 512/NT accumulator blocks (one per output plane in flight); mode 2 a ring of 3
+  // sets x 4 parity classes.
   constexpr int kSetCols = G::ACCS * NT;
-  constexpr int kTmemCols = (G::NSETS * kSetCols <= 32) ? 32 : (G::NSETS * kSetCols <= 64) ? 64 : (G::NSETS * kSetCols <= 128) ? 128 : (G::NSETS * kSetCols <= 256) ? 256 : 512;
-  static_assert(G::NSETS * kSetCols <= 512, "TMEM overflow");
+  constexpr int R = (MODE == 2) ? 3 : 512 / NT;
+  constexpr int kTmemCols = 512;
+  static_assert(R * kSetCols <= 512 && R <= kMaxSets, "TMEM ring overflow");
 
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
   uint8_t* slots_s = smem + ((w_bytes + 127) & ~127u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(slots_s + (size_t)p.nslots * kSlotBytes);
-  uint64_t* full_bar = bars;                           // [nslots]   producers -> MMA
-  uint64_t* empty_bar = bars + kMaxSlots;              // [nslots]   MMA (commit) -> producers
-  uint64_t* tfull_bar = bars + 2 * kMaxSlots;          // [NSETS]    MMA (commit) -> epilogue
-  uint64_t* tempty_bar = bars + 2 * kMaxSlots + kMaxSets;  // [NSETS] epilogue -> MMA
+  uint64_t* full_bar = bars;                               // [nslots] producers -> MMA
+  uint64_t* empty_bar = bars + kMaxSlots;                  // [nslots] MMA (commit) -> producers
+  uint64_t* tfull_bar = bars + 2 * kMaxSlots;              // [R]      MMA (commit) -> epilogue
+  uint64_t* tempty_bar = bars + 2 * kMaxSlots + kMaxSets;  // [R]      epilogue -> MMA
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxSets);
 
   if (threadIdx.x == 0) {
@@ -231,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
       mbar_init(smem_u32(full_bar + i), kProdWarps);
       mbar_init(smem_u32(empty_bar + i), 1);
     }
-    for (int i = 0; i < G::NSETS; ++i) {
+    for (int i = 0; i < R; ++i) {
       mbar_init(smem_u32(tfull_bar + i), 1);
       mbar_init(smem_u32(tempty_bar + i), kEpiWarps);
     }
@@ -257,13 +307,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (MODE != 2 && warp < kEpiWarps) {
+    // depth-stacked MMAs always accumulate: every accumulator block starts at zero (and is re-zeroed by the epilogue)
+    for (int c = 0; c < 512; c += 32) tmem_zero<32>(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp >= kEpiWarps + 1) {
     // =========================================================== PRODUCERS
     const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;  // 0..127
-    uint32_t stage = 0;                                   // global stage counter (ring position + phase)
-    bool pending = false;
-    uint32_t pending_slot = 0;
+    uint32_t stage = 0;  // global stage counter (ring position + phase)
+    // Up to `la` stages of cp.async groups are kept in flight per thread (la = min(4, nslots - 1)); a stage is
+    // published (fence.proxy.async + mbarrier arrive) when its group has landed.
+    const int la = min(4, p.nslots - 1);
+    uint32_t issued = 0, published = 0;
+    auto publish_one = [&](int allow_in_flight) {
+      switch (allow_in_flight) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        default: cp_async_wait<4>(); break;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(full_bar + (published % p.nslots)));
+      ++published;
+    };
     for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
       const Item it = decode_item(p, nb_of_cta * per_nb + li);
       int p0, p1, o0, o1;
@@ -291,105 +364,160 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
             cp_async16(sbase + kc * kChunkStride + sv * 16, src, ok ? 16u : 0u);
           }
           cp_async_commit();
-          if (pending) {  // publish the previous stage while this one is in flight
-            cp_async_wait<1>();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(full_bar + pending_slot));
-          }
-          pending = true;
-          pending_slot = slot;
+          ++issued;
+          if ((int)(issued - published) > la) publish_one(la);
         }
       }
     }
-    if (pending) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(full_bar + pending_slot));
-    }
+    while (published < issued) publish_one((int)(issued - published) - 1);
   } else if (warp == kEpiWarps) {
-    // =========================================================== MMA ISSUER (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(NT);
-      const uint32_t w_base = smem_u32(w_s);
-      uint32_t stage = 0, job_base = 0;  // job = output plane; set = job % NSETS
-      for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
-        const Item it = decode_item(p, nb_of_cta * per_nb + li);
-        int p0, p1, o0, o1;
-        chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
-        for (int pl = p0; pl <= p1; ++pl) {
+    // =========================================================== MMA ISSUER
+    // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; a single
+    // elected lane issues tcgen05.mma / tcgen05.commit.
+    const uint32_t w_base = smem_u32(w_s);
+    const uint32_t a_hi = desc_hi(G::ROW * 16);
+    const uint32_t b_hi = desc_hi(128);
+    // mode 0/1: accumulator block of output plane od = od - o0 (chunk <= R, so the depth-stacked window never wraps:
+    // switching the accumulator address between consecutive MMAs costs ~230 cycles, measured with tools/umma_bench.cu).
+    // use_mask holds the mbarrier phase parity of every block (toggled per use).  mode 2: set = job % R.
+    uint32_t stage = 0, job_base = 0, use_mask = 0;
+    uint32_t slot = 0, phase = 0;
+    long long dbg_tempty = 0, dbg_full = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    int dbg_nst = 0;
+    const uint32_t a_lo0 = desc_lo(smem_u32(slots_s), kChunkStride);
+    const uint32_t b_lo0 = desc_lo(w_base, (MODE == 2 ? 1 : 3) * NT * 16);
+    uint32_t a_lo = a_lo0;
+    for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
+      const Item it = decode_item(p, nb_of_cta * per_nb + li);
+      int p0, p1, o0, o1;
+      chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+      const int nout = o1 - o0;
+      int next_new = 0, next_done = 0;
+      for (int pl = p0; pl <= p1; ++pl) {
+        if (MODE != 2) {
+          // ---- depth-stacked issue: output blocks [oa, ob] (relative to o0) fed by this input plane, weight blocks
+          //      [wb_a, wb_a + nb).  The issuing warp is latency-bound on its own instruction stream (a 56-cycle MMA
+          //      leaves ~12 instructions of budget), so the bookkeeping below is kept to a few integer ops per plane.
+          int oa, ob, wb_a;
+          if (MODE == 0) {
+            const int rel = pl - o0;
+            oa = max(rel - 1, 0), ob = min(rel + 1, nout - 1), wb_a = oa - rel + 1;
+          } else {
+            const int rel2 = pl - (2 * o0 - 1);
+            if (!(rel2 & 1)) {
+              const int od1 = (rel2 >> 1) - 1;
+              oa = max(od1, 0), ob = min(od1 + 1, nout - 1), wb_a = oa - od1;
+            } else {
+              oa = ob = rel2 >> 1, wb_a = 2;
+            }
+          }
+          const uint32_t i1 = make_idesc((ob - oa + 1) * NT);
+          const uint32_t d1 = tmem_base + (uint32_t)oa * NT;
+          long long c0 = p.dbg ? clock64() : 0;
+          for (; next_new <= ob; ++next_new) {  // first touch of a block: the epilogue must have drained + zeroed it
+            mbar_wait(smem_u32(tempty_bar + next_new), ((use_mask >> next_new) & 1) ^ 1);
+            use_mask ^= 1u << next_new;
+          }
+          if (p.dbg) dbg_tempty += clock64() - c0;
+          for (int kh = 0; kh < KH; ++kh) {
+            c0 = p.dbg ? clock64() : 0;
+            mbar_wait(smem_u32(full_bar + slot), phase);
+            if (p.dbg) {
+              dbg_full += clock64() - c0;
+              if (blockIdx.x < 4 && dbg_nst < 60 && lane == 0) p.dbg[8 * gridDim.x + blockIdx.x * 64 + dbg_nst] = clock64() - dbg_t0;
+              ++dbg_nst;
+            }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b0 = b_lo0 + (uint32_t)kh * ((27 * 4 * NT * 16) >> 4) + (uint32_t)wb_a * ((NT * 16) >> 4);
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const int th_ = t / 3, tw_ = t % 3;
+                const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_)
+                                                  : (uint32_t)((((th_ & 1) << 1) | (tw_ & 1)) * 153 + (th_ >> 1) * 9 + (tw_ >> 1));
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                  umma_bf16_lh(d1, a_lo + ((ks * 2 * kChunkStride + voff * 16) >> 4), a_hi, b0 + (((uint32_t)(t * 4 + ks * 2) * (3 * NT * 16)) >> 4), b_hi,
+                               i1, 1u);
+              }
+              if (kh == KH - 1) {
+                // block b is complete after its last contributing plane: o0+b+1 (mode 0) / 2(o0+b)+1 (mode 1), or the item's last plane
+                for (int nd = next_done; nd <= ob && (pl == p1 || pl == ((MODE == 0) ? o0 + nd + 1 : 2 * (o0 + nd) + 1)); ++nd)
+                  umma_commit(smem_u32(tfull_bar + nd));
+              }
+              umma_commit(smem_u32(empty_bar + slot));  // stage consumed -> producers may refill it
+            }
+            __syncwarp();
+            if (++slot == (uint32_t)p.nslots) slot = 0, phase ^= 1, a_lo = a_lo0;
+            else a_lo += kSlotBytes >> 4;
+          }
+          while (next_done <= ob && (pl == p1 || pl == ((MODE == 0) ? o0 + next_done + 1 : 2 * (o0 + next_done) + 1))) ++next_done;
+        } else {
+          // ---- transposed conv: per output plane a set of 4 parity-class accumulators
           for (int kh = 0; kh < KH; ++kh, ++stage) {
             const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
             mbar_wait(smem_u32(full_bar + slot), phase);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(slots_s + (size_t)slot * kSlotBytes);
+            const uint32_t a0 = desc_lo(smem_u32(slots_s + (size_t)slot * kSlotBytes), kChunkStride);
+            constexpr uint32_t idesc = make_idesc(NT);
 #pragma unroll 1
-            for (int kq = 0; kq < 3; ++kq) {  // oldest output plane first
-              const int kd = (MODE == 2) ? kq : 2 - kq;
-              const int od = out_plane<MODE>(pl, kd);
+            for (int kd = 0; kd < 3; ++kd) {  // oldest output plane first
+              const int od = 2 * pl - 1 + kd;
               if (od < o0 || od >= o1) continue;
               int first, last;
               contrib_range<MODE>(p, od, first, last);
               const uint32_t job = job_base + (uint32_t)(od - o0);
-              const uint32_t set = job % G::NSETS;
-              if (pl == first && kh == 0) {  // first touch of this accumulator set: wait until the epilogue drained it
-                mbar_wait(smem_u32(tempty_bar + set), ((job / G::NSETS) & 1) ^ 1);
+              const uint32_t set = job % R;
+              const bool fresh = (pl == first && kh == 0);
+              if (fresh) {
+                mbar_wait(smem_u32(tempty_bar + set), ((job / R) & 1) ^ 1);
                 tc_fence_after();
               }
-              const uint32_t d_base = tmem_base + set * kSetCols;
-              const uint32_t wk = w_base + (uint32_t)(kh * 27 + kd * 9) * (4 * NT * 16);
-              if (MODE != 2) {
-                uint32_t acc = !(pl == first && kh == 0);
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                  const int th_ = t / 3, tw_ = t % 3;
-                  const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_)
-                                                    : (uint32_t)((((th_ & 1) << 1) | (tw_ & 1)) * 153 + (th_ >> 1) * 9 + (tw_ >> 1));
-#pragma unroll
-                  for (int ks = 0; ks < 2; ++ks) {
-                    const uint64_t ad = make_desc(a_base + ks * 2 * kChunkStride + voff * 16, kChunkStride, G::ROW * 16);
-                    const uint64_t bd = make_desc(wk + (uint32_t)(t * 4 + ks * 2) * (NT * 16), NT * 16, 128);
-                    umma_bf16(d_base, ad, bd, idesc, acc);
-                    acc = 1;
-                  }
-                }
-              } else {
-                // transposed conv: output parity class (ph, pw) <- taps kh_ in {1} (ph=0) or {2 (dh=0), 0 (dh=1)} (ph=1)
+              if (elect_one()) {
+                const uint32_t d_base = tmem_base + set * kSetCols;
+                const uint32_t b0 = desc_lo(w_base + (uint32_t)(kh * 27 + kd * 9) * (4 * NT * 16), NT * 16);
 #pragma unroll
                 for (int cls = 0; cls < 4; ++cls) {
                   const int ph = cls >> 1, pw = cls & 1;
-                  uint32_t acc = !(pl == first && kh == 0);
+                  uint32_t acc = fresh ? 0u : 1u;
 #pragma unroll
                   for (int ih = 0; ih <= ph; ++ih) {
 #pragma unroll
                     for (int iw = 0; iw <= pw; ++iw) {
+                      // output parity 0 <- tap 1 (same index); parity 1 <- tap 2 (same index) and tap 0 (index + 1)
                       const int th_ = ph ? (ih ? 0 : 2) : 1, tw_ = pw ? (iw ? 0 : 2) : 1;
-                      const uint32_t voff = (uint32_t)(ih * 9 + iw);
 #pragma unroll
                       for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t ad = make_desc(a_base + ks * 2 * kChunkStride + voff * 16, kChunkStride, G::ROW * 16);
-                        const uint64_t bd = make_desc(wk + (uint32_t)((th_ * 3 + tw_) * 4 + ks * 2) * (NT * 16), NT * 16, 128);
-                        umma_bf16(d_base + cls * NT, ad, bd, idesc, acc);
-                        acc = 1;
+                        const uint32_t a_lo = a0 + ((ks * 2 * kChunkStride + (uint32_t)(ih * 9 + iw) * 16) >> 4);
+                        const uint32_t b_lo = b0 + (((uint32_t)((th_ * 3 + tw_) * 4 + ks * 2) * (NT * 16)) >> 4);
+                        umma_bf16_lh(d_base + cls * NT, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                        acc = 1u;
                       }
                     }
                   }
                 }
+                if (pl == last && kh == KH - 1) umma_commit(smem_u32(tfull_bar + set));
               }
-              if (pl == last && kh == KH - 1) umma_commit(smem_u32(tfull_bar + set));  // accumulator complete -> epilogue
+              __syncwarp();
             }
-            umma_commit(smem_u32(empty_bar + slot));  // stage consumed -> producers may refill it
+            if (elect_one()) umma_commit(smem_u32(empty_bar + slot));
+            __syncwarp();
           }
         }
-        job_base += (uint32_t)(o1 - o0);
       }
+      job_base += (uint32_t)(o1 - o0);
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = dbg_tempty;
+      p.dbg[blockIdx.x * 8 + 5] = dbg_full;
+      p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_t0;
     }
   } else {
     // =========================================================== EPILOGUE (4 warps = 128 rows)
     const int row = warp * 32 + lane;  // TMEM lane == GEMM row == tile position
     const int hl = row >> 3, wl = row & 7;
-    uint32_t job_base = 0;
+    uint32_t job_base = 0, use_mask = 0;
+    long long dbg_tfull = 0;
     for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
       const Item it = decode_item(p, nb_of_cta * per_nb + li);
       int p0, p1, o0, o1;
@@ -397,8 +525,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
       const int n0 = it.nb * NT;
       for (int od = o0; od < o1; ++od) {
         const uint32_t job = job_base + (uint32_t)(od - o0);
-        const uint32_t set = job % G::NSETS;
-        mbar_wait(smem_u32(tfull_bar + set), (job / G::NSETS) & 1);
+        uint32_t set, par;
+        if (MODE != 2) {
+          set = (uint32_t)(od - o0), par = (use_mask >> set) & 1;
+          use_mask ^= 1u << set;
+        } else {
+          set = job % R, par = (job / R) & 1;
+        }
+        const long long e0 = p.dbg ? clock64() : 0;
+        mbar_wait(smem_u32(tfull_bar + set), par);
+        if (p.dbg) dbg_tfull += clock64() - e0;
         tc_fence_after();
 #pragma unroll 1
         for (int cls = 0; cls < G::ACCS; ++cls) {
@@ -409,6 +545,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
           else
             tmem_ld16(taddr, v);
           tmem_ld_wait();
+          if (MODE != 2) tmem_zero<NT>(taddr);  // hand the block back zeroed (completion awaited below)
           int oh, ow;
           bool ok;
           if (MODE == 2) {
@@ -471,17 +608,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
             }
           }
         }
+        if (MODE != 2) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(tempty_bar + set));
       }
       job_base += (uint32_t)(o1 - o0);
     }
+    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 7] = dbg_tfull;
   }
 
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (p.dbg != nullptr && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    p.dbg[blockIdx.x * 8 + 0] = smid;
+    p.dbg[blockIdx.x * 8 + 1] = t_start;
+    p.dbg[blockIdx.x * 8 + 2] = t1;
+    p.dbg[blockIdx.x * 8 + 3] = (per_nb - lane_cta + ctas_per_nb - 1) / ctas_per_nb;
+  }
   if (warp == kEpiWarps) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
@@ -490,20 +639,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
 // weights (Co,Ci,3,3,3) [mode 0/1] or (Ci,Co,3,3,3) [mode 2], fp32 -> [nblk][khalf][27][4][NT][8] bf16, zero padded
 __global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Ci, int Co, int NT, int nblk, int mode,
                                 long long total) {
+  // mode 2:   [nblk][khalf][tap 27][kc 4][NT][8]
+  // mode 0/1: [nblk][khalf][tap 9 (kh,kw)][kc 4][depth block 3][NT][8]   (see wblock_of_kd)
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     long long r = e;
     const int j = (int)(r % 8);
     r /= 8;
     const int n = (int)(r % NT);
     r /= NT;
-    const int kc = (int)(r % 4);
-    r /= 4;
-    const int t = (int)(r % 27);
-    r /= 27;
+    int kd, t9, kc;
+    if (mode == 2) {
+      kc = (int)(r % 4);
+      r /= 4;
+      const int t = (int)(r % 27);
+      r /= 27;
+      kd = t / 9, t9 = t % 9;
+    } else {
+      const int blk = (int)(r % 3);
+      r /= 3;
+      kc = (int)(r % 4);
+      r /= 4;
+      t9 = (int)(r % 9);
+      r /= 9;
+      kd = 0;
+      for (int k = 0; k < 3; ++k)
+        if (wblock_of_kd(mode, k) == blk) kd = k;
+    }
     const int KH = Ci / kStageCh;
     const int kh = (int)(r % KH);
     const int nb = (int)(r / KH);
-    const int co = nb * NT + n, ci = kh * kStageCh + kc * 8 + j;
+    const int co = nb * NT + n, ci = kh * kStageCh + kc * 8 + j, t = kd * 9 + t9;
     float v = 0.f;
     if (co < Co) v = (mode == 2) ? w[((size_t)ci * Co + co) * 27 + t] : w[((size_t)co * Ci + ci) * 27 + t];
     wp[e] = float_to_bf16_bits(v);
@@ -525,6 +690,13 @@ int launch_tc(const TcParams& p, int grid, size_t smem, cudaStream_t s) {
 }
 
 }  // namespace
+
+static long long* g_tc_dbg = nullptr;
+// profiling aid (not part of the reference surface): per-CTA {smid, start ns, end ns, items} records of the next launches
+extern "C" int mode_conv3d_set_debug_buffer(void* dev_ptr) {
+  g_tc_dbg = (long long*)dev_ptr;
+  return MODE_OK;
+}
 
 extern "C" size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode) {
   (void)mode;
@@ -557,6 +729,7 @@ extern "C" int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, c
   MODE_CHECK_ARG(!(mode == 2 && NT != 32), "conv3d_bf16: transposed conv needs Co %% 32 == 0");
   TcParams p;
   p.x = x, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.res_f32 = residual_f32, p.out = out, p.out_f32 = out_f32;
+  p.dbg = g_tc_dbg;
   p.B = B, p.Cin = Ci, p.Co = Co, p.CoReal = Co, p.Di = Di, p.Hi = Hi, p.Wi = Wi, p.relu = relu;
   if (mode == 0) {
     p.Do = Di, p.Ho = Hi, p.Wo = Wi;
@@ -572,25 +745,28 @@ extern "C" int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, c
   const int KH = Ci / kStageCh;
   const size_t w_bytes = ((size_t)KH * 27 * 4 * NT * 16 + 127) & ~(size_t)127;
   const size_t slot_bytes = (size_t)(mode == 0 ? Geo<0>::NV : mode == 1 ? Geo<1>::NV : Geo<2>::NV) * kStageCh * 2;
-  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16;
+  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128;
   const size_t budget = 227 * 1024;
   int nslots = (int)std::min<size_t>(kMaxSlots, (budget - w_bytes - misc) / slot_bytes);
   MODE_CHECK_ARG(nslots >= 2, "conv3d_bf16: not enough shared memory for a 2-stage pipeline");
   p.nslots = nslots;
-  // depth chunking: choose the chunk that maximises (wave efficiency) x (halo efficiency)
+  // depth chunking: split the depth range into nch BALANCED chunks (chunk = ceil(d / nch)); pick the nch that minimises
+  // the critical-path stage count  rounds x (chunk + halo)  (persistent CTAs, round-robin items).
   const long long cols = (long long)B * p.tiles_h * p.tiles_w;
   const int halo = (mode == 0) ? 2 : 1;
-  int best_chunk = d_dim;
-  double best = -1;
-  for (int c = 1; c <= d_dim; ++c) {
-    const int nch = ceil_div(d_dim, c);
-    const long long items = cols * nch;
+  const int max_chunk = (mode == 2) ? d_dim : 512 / NT;  // mode 0/1: one TMEM accumulator block per output plane of the chunk
+  int best_chunk = std::min(d_dim, max_chunk);
+  double best = 1e30;
+  for (int nch = 1; nch <= d_dim; ++nch) {
+    const int c = ceil_div(d_dim, nch);
+    if (c > max_chunk) continue;
+    const int nch_eff = ceil_div(d_dim, c);
+    const long long items = cols * nch_eff;
     const long long ctas = std::min<long long>(items, kNumSMs / p.nblk);
     const long long rounds = (items + ctas - 1) / ctas;
-    const double wave_eff = (double)items / (double)(rounds * (kNumSMs / p.nblk));
-    const double halo_eff = (double)c / (double)(c + halo);
-    const double score = wave_eff * halo_eff;
-    if (score > best + 1e-9) best = score, best_chunk = c;
+    const double stages = (double)(mode == 1 ? 2 * c + halo : c + halo);
+    const double cost = (double)rounds * (stages + 1.5);  // +1.5: per-item pipeline ramp
+    if (cost < best - 1e-9) best = cost, best_chunk = c;
   }
   p.chunk = best_chunk;
   p.nchunks = ceil_div(d_dim, p.chunk);

@@ -74,7 +74,10 @@ def main():
     layers = [('64->32 s1 @48x256x128', 0, 64, 32, (48, 256, 128)), ('32->32 s1 @48x256x128', 0, 32, 32, (48, 256, 128)), ('32->64 s2 @48x256x128', 1, 32, 64, (48, 256, 128)),
               ('64->64 s1 @24x128x64', 0, 64, 64, (24, 128, 64)), ('64->64 s2 @24x128x64', 1, 64, 64, (24, 128, 64)), ('64->64 s1 @12x64x32', 0, 64, 64, (12, 64, 32)),
               ('64->64 deconv @12x64x32', 2, 64, 64, (12, 64, 32)), ('64->32 deconv @24x128x64', 2, 64, 32, (24, 128, 64)), ('32->1 s1 @48x256x128', 0, 32, 1, (48, 256, 128))]
+    only = os.environ.get('LAYER')
     for name, mode, ci, co, dims in layers:
+      if only and only not in name:
+        continue
       x = torch.randn(1, *dims, ci, device=dev).bfloat16()
       w = torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), device=dev) / math.sqrt(27 * ci)
       wp = ops.conv3d_pack_weights(w, mode)

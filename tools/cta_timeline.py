@@ -1,0 +1,48 @@
+"""Per-CTA timeline of one conv3d_bf16 launch (profiling aid): who ran where, for how long."""
+import ctypes, math, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mode_2022_b200 import ops, _lib
+lib = _lib.load()
+dev = 'cuda'
+ci, co, dims, mode = 32, 32, (48, 256, 128), 0
+x = torch.randn(1, *dims, ci, device=dev).bfloat16()
+w = torch.randn(co, ci, 3, 3, 3, device=dev) / math.sqrt(27 * ci)
+wp = ops.conv3d_pack_weights(w, mode)
+for _ in range(3):
+  ops.conv3d_bf16(x, wp, co, None, None, None, mode, True, False)
+dbg = torch.zeros(148 * 8 + 4 * 64, dtype=torch.int64, device=dev)
+lib.mode_conv3d_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
+torch.cuda.synchronize()
+ops.conv3d_bf16(x, wp, co, None, None, None, mode, True, False)
+torch.cuda.synchronize()
+lib.mode_conv3d_set_debug_buffer(ctypes.c_void_p(0))
+st = dbg[148 * 8:].view(4, 64).cpu()
+d = dbg[:148 * 8].view(148, 8).cpu()
+t0 = d[:, 1].min().item()
+dur = (d[:, 2] - d[:, 1]).float() / 1e3
+start = (d[:, 1] - t0).float() / 1e3
+print('CTAs', d.shape[0], 'distinct SMs', len(set(d[:, 0].tolist())))
+print('start offset us: min %.1f max %.1f' % (start.min(), start.max()))
+print('duration us: min %.1f median %.1f max %.1f' % (dur.min(), dur.median(), dur.max()))
+print('end us: max %.1f' % ((d[:, 2] - t0).float().max() / 1e3))
+order = torch.argsort(dur)
+for i in list(order[:5]) + list(order[-5:]):
+  print('cta %3d sm %3d start %.1f dur %.1f items %d' % (i, d[i, 0], start[i], dur[i], d[i, 3]))
+import collections
+c = collections.Counter(d[:, 0].tolist())
+print('SMs with >1 CTA:', {k: v for k, v in c.items() if v > 1})
+print('dur by cta id (us):')
+print(' '.join('%d' % round(v) for v in dur.tolist()))
+sm = d[:, 0].tolist()
+bysm = sorted(zip(sm, dur.tolist()))
+print('dur by smid:')
+print(' '.join('%d:%d' % (a, round(b)) for a, b in bysm))
+
+print('MMA warp cycles: cta, total, wait_tempty, wait_full | epilogue warp0 wait_tfull')
+for i in (0, 1, 2, 3, 4, 5, 6, 7, 144, 145, 146, 147):
+  print(i, d[i, 6].item(), d[i, 4].item(), d[i, 5].item(), '|', d[i, 7].item())
+
+for c in range(4):
+  ts = st[c, :60].tolist()
+  print('cta', c, 'stage deltas (cycles):', ' '.join(str(int(b - a)) for a, b in zip(ts[:-1], ts[1:])))
