@@ -60,9 +60,21 @@ def load() -> C.CDLL:
   return lib
 
 
+# optional per-call CUDA-event profiler (bench.py roofline leg): list of (name, start_event, end_event)
+PROFILE = None
+
+
 def call(name: str, *args) -> None:
   lib = load()
-  rc = getattr(lib, name)(*args)
+  if PROFILE is not None:
+    import torch
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = getattr(lib, name)(*args)
+    b.record()
+    PROFILE.append((name, args, a, b))
+  else:
+    rc = getattr(lib, name)(*args)
   if rc != 0:
     raise RuntimeError(f'{name} failed ({rc}): {lib.mode_b200_last_error().decode()}')
 
