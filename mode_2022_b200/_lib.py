@@ -33,7 +33,7 @@ SIGNATURES = {
 }
 OTHER_SYMBOLS = ['mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
 
-PENDING = {'mode_sphere_conv_bf16', 'mode_sphere_conv_pack_weights'}  # TODO remove
+PENDING = set()
 _lib = None
 
 

@@ -1,0 +1,321 @@
+// sphere_conv_tc.cu -- spherical convolution forward on tcgen05 tensor cores: the tangent-plane bilinear gather is
+// fused into the operand staging of an implicit GEMM, so the reference's 151 MB column buffer never exists.
+//
+// Reference: sphere_conv_forward_cuda (sphere_conv_cuda.cpp:129-210) = sphere_im2col_gpu_kernel
+// (sphere_conv_cuda_kernel.cu:195-262, bilinear :83-113) + addmm_ per batch element.
+//
+//   out[b, pix, o] = sum_{k, c} bilinear(x[b, :, :, c], pos[2k, pix], pos[2k+1, pix]) * W[o, c, k]
+//
+// GEMM view: M = 128 consecutive pixels (NHWC), N = Co, K = 9 taps x C.  For every (tap, 64-channel half) stage the
+// 8 gather warps blend the four corner pixels (fp32 arithmetic, reference expression order w1*v1+w2*v2+w3*v3+w4*v4,
+// reference edge rules: tap dropped unless -1 < h < H and -1 < w < W, each corner dropped when outside the image, no
+// longitude wrap) into a bf16 A tile laid out for UMMA ("interleave" K-major: [8-channel chunk][pixel][16 B], chunk
+// stride padded to 2064 B so the 128-bit shared stores are conflict free), the matching 16 KB weight slab is fetched
+// with cp.async, and one elected thread issues 4 x tcgen05.mma (M=128, N=Co, K=16) into a TMEM accumulator.  The same
+// warps run the epilogue (BN affine + residual + ReLU, bf16 NHWC store).
+//
+// The kernel is gather-bound, not MMA-bound: per 128-pixel tile the corner loads alone are 128 x 9 x 4 x 256 B =
+// 1.18 MB of L1 traffic (~9.2k wavefront cycles) against 4.6k MMA cycles; two CTAs per SM keep both units busy.
+#include "common.cuh"
+using namespace mode;
+
+namespace {
+
+constexpr int kGatherWarps = 8;
+constexpr int kThreadsS = (kGatherWarps + 1) * 32;  // 288
+constexpr int kStagesS = 3;
+constexpr int kChunkStrideA = 128 * 16 + 16;             // 2064 B: +16 B pad -> conflict-free STS.128 from 8 chunk-lanes
+constexpr int kABytes = ((8 * kChunkStrideA) + 127) & ~127;  // 16640
+
+struct ScParams {
+  const uint16_t* x;    // (B,H,W,C) bf16
+  const float* pos;     // (18,H,W) fp32
+  const uint16_t* wpk;  // [9][C/64][8][Co][8] bf16
+  const float* scale;
+  const float* shift;
+  const uint16_t* res;  // (B,H,W,Co) bf16 or null
+  uint16_t* out;        // (B,H,W,Co) bf16
+  int B, C, H, W, Co, relu;
+  long long npix;       // B*H*W
+  int ntiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > (1u << 24)) {
+      printf("sphere_conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14); }
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+
+__global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_bytes = (uint32_t)p.Co * 64 * 2;          // one weight slab: Co x 64 ch
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStagesS * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStagesS;
+  uint64_t* tfull_bar = bars + 2 * kStagesS;
+  uint64_t* tempty_bar = bars + 2 * kStagesS + 1;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStagesS + 2);
+  const int tmem_cols = p.Co <= 32 ? 32 : p.Co <= 64 ? 64 : p.Co <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesS; ++i) {
+      mbar_init(smem_u32(full_bar + i), kGatherWarps);
+      mbar_init(smem_u32(empty_bar + i), 1);
+    }
+    mbar_init(smem_u32(tfull_bar), 1);
+    mbar_init(smem_u32(tempty_bar), kGatherWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kGatherWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int HW = p.H * p.W;
+  const int nhalf = p.C / 64;
+  const int nstage_tile = 9 * nhalf;
+
+  if (warp < kGatherWarps) {
+    // =================================================== gather producers (+ epilogue)
+    const int tid = threadIdx.x;  // 0..255
+    const int kc = tid & 7;       // 8-channel chunk inside the 64-channel half
+    uint32_t stage = 0, tile_n = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_n) {
+      for (int k = 0; k < 9; ++k) {
+        // per-(pixel, tap) sampling parameters for this thread's 4 pixels
+        float w1[4], w2[4], w3[4], w4[4];
+        long long o1[4], o2[4], o3[4], o4[4];  // element offsets of the four corners (-1 = dropped)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long gp = (long long)tile * 128 + (tid >> 3) + 32 * j;
+          o1[j] = o2[j] = o3[j] = o4[j] = -1;
+          w1[j] = w2[j] = w3[j] = w4[j] = 0.f;
+          if (gp < p.npix) {
+            const int b = (int)(gp / HW), pp = (int)(gp - (long long)b * HW);
+            const float h_im = __ldg(p.pos + (size_t)(2 * k) * HW + pp);
+            const float w_im = __ldg(p.pos + (size_t)(2 * k + 1) * HW + pp);
+            if (h_im > -1 && w_im > -1 && h_im < p.H && w_im < p.W) {  // kernel.cu:246
+              const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+              const int h_high = h_low + 1, w_high = w_low + 1;
+              const float lh = h_im - h_low, lw = w_im - w_low, hh = 1 - lh, hw = 1 - lw;
+              w1[j] = hh * hw, w2[j] = hh * lw, w3[j] = lh * hw, w4[j] = lh * lw;  // kernel.cu:109
+              const long long base = (long long)b * HW;
+              if (h_low >= 0 && w_low >= 0) o1[j] = (base + (long long)h_low * p.W + w_low) * p.C;
+              if (h_low >= 0 && w_high <= p.W - 1) o2[j] = (base + (long long)h_low * p.W + w_high) * p.C;
+              if (h_high <= p.H - 1 && w_low >= 0) o3[j] = (base + (long long)h_high * p.W + w_low) * p.C;
+              if (h_high <= p.H - 1 && w_high <= p.W - 1) o4[j] = (base + (long long)h_high * p.W + w_high) * p.C;
+            }
+          }
+        }
+        for (int half = 0; half < nhalf; ++half, ++stage) {
+          const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
+          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+          uint8_t* a_s = smem + (size_t)slot * stage_bytes;
+          const uint32_t b_s = smem_u32(a_s + kABytes);
+          // weight slab (tap k, half): contiguous b_bytes in the packed layout
+          {
+            const uint16_t* wsrc = p.wpk + ((size_t)(k * nhalf + half) * b_bytes) / 2;
+            for (uint32_t i = tid; i < b_bytes / 16; i += kGatherWarps * 32) cp_async16(b_s + i * 16, wsrc + i * 8);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+          }
+          const int coff = half * 64 + kc * 8;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            const uint4 v1 = o1[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o1[j] + coff)) : z;
+            const uint4 v2 = o2[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o2[j] + coff)) : z;
+            const uint4 v3 = o3[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o3[j] + coff)) : z;
+            const uint4 v4 = o4[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o4[j] + coff)) : z;
+            const uint32_t a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w},
+                           a4[4] = {v4.x, v4.y, v4.z, v4.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float lo = (w1[j] * __uint_as_float(a1[q] << 16) + w2[j] * __uint_as_float(a2[q] << 16) + w3[j] * __uint_as_float(a3[q] << 16) +
+                                w4[j] * __uint_as_float(a4[q] << 16));
+              const float hi = (w1[j] * __uint_as_float(a1[q] & 0xFFFF0000u) + w2[j] * __uint_as_float(a2[q] & 0xFFFF0000u) +
+                                w3[j] * __uint_as_float(a3[q] & 0xFFFF0000u) + w4[j] * __uint_as_float(a4[q] & 0xFFFF0000u));
+              o[q] = pack_bf16x2(lo, hi);
+            }
+            const int pix_l = (tid >> 3) + 32 * j;
+            *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
+        }
+      }
+      // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns [64*(w/4), +64)
+      mbar_wait(smem_u32(tfull_bar), tile_n & 1);
+      tc_fence_after();
+      const int q = warp & 3, hcol = warp >> 2;
+      const long long gp = (long long)tile * 128 + q * 32 + lane;
+      for (int c0 = hcol * (p.Co / 2); c0 < (hcol + 1) * (p.Co / 2); c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (gp < p.npix) {
+          const uint16_t* rp = p.res ? p.res + gp * p.Co + c0 : nullptr;
+          uint16_t* op = p.out + gp * p.Co + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[g * 8 + e]);
+            if (p.scale) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + g * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + g * 8) + 1);
+              y[0] *= s0.x, y[1] *= s0.y, y[2] *= s0.z, y[3] *= s0.w, y[4] *= s1.x, y[5] *= s1.y, y[6] *= s1.z, y[7] *= s1.w;
+            }
+            if (p.shift) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8) + 1);
+              y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
+            }
+            if (rp) {
+              const uint4 r = ld_nc_v4(rp + g * 8);
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) y[2 * e] += __uint_as_float(rr[e] << 16), y[2 * e + 1] += __uint_as_float(rr[e] & 0xFFFF0000u);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+            }
+            *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar));
+    }
+  } else {
+    // =================================================== MMA issuer (warp-uniform control flow, one elected lane issues)
+    const uint32_t idesc = make_idesc(p.Co);
+    const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
+    uint32_t stage = 0, tile_n = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_n) {
+      mbar_wait(smem_u32(tempty_bar), (tile_n & 1) ^ 1);  // epilogue of the previous tile has drained the accumulator
+      tc_fence_after();
+      for (int s = 0; s < nstage_tile; ++s, ++stage) {
+        const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
+        mbar_wait(smem_u32(full_bar + slot), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = desc_lo(smem_u32(smem + (size_t)slot * stage_bytes), kChunkStrideA);
+          const uint32_t b0 = desc_lo(smem_u32(smem + (size_t)slot * stage_bytes + kABytes), (uint32_t)p.Co * 16);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma(tmem_base, a0 + ((ks * 2 * kChunkStrideA) >> 4), a_hi, b0 + ((uint32_t)(ks * 2 * p.Co * 16) >> 4), b_hi, idesc, (s | ks) ? 1u : 0u);
+          umma_commit(smem_u32(empty_bar + slot));
+          if (s == nstage_tile - 1) umma_commit(smem_u32(tfull_bar));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
+// (Co, C, 3, 3) fp32 -> [tap 9][half C/64][chunk 8][n Co][8] bf16
+__global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int C, int Co, long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    const int j = (int)(r % 8);
+    r /= 8;
+    const int n = (int)(r % Co);
+    r /= Co;
+    const int kc = (int)(r % 8);
+    r /= 8;
+    const int half = (int)(r % (C / 64));
+    const int k = (int)(r / (C / 64));
+    const int c = half * 64 + kc * 8 + j;
+    wp[e] = float_to_bf16_bits(w[((size_t)n * C + c) * 9 + k]);
+  }
+}
+
+}  // namespace
+
+extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_bf16* w_packed, int C, int Co, void* stream) {
+  MODE_CHECK_ARG(w && w_packed, "sphere_conv_pack_weights: null pointer");
+  MODE_CHECK_ARG(C > 0 && C % 64 == 0 && Co >= 16 && Co <= 256 && Co % 16 == 0, "sphere_conv_pack_weights: need C %% 64 == 0 and Co %% 16 == 0, Co <= 256");
+  const long long total = 9LL * C * Co;
+  pack_wsphere_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, C, Co, total);
+  MODE_CHECK_LAUNCH("sphere_conv_pack_weights");
+  return MODE_OK;
+}
+
+extern "C" int mode_sphere_conv_bf16(const mode_bf16* x, const float* pos, const mode_bf16* w_packed, const float* scale, const float* shift,
+                                     const mode_bf16* residual, mode_bf16* out, int B, int C, int H, int W, int Co, int relu, void* stream) {
+  MODE_CHECK_ARG(x && pos && w_packed && out, "sphere_conv_bf16: null pointer");
+  MODE_CHECK_ARG(B > 0 && H > 0 && W > 0, "sphere_conv_bf16: bad shape");
+  MODE_CHECK_ARG(C > 0 && C % 64 == 0, "sphere_conv_bf16: C (%d) must be a multiple of 64 (use the f32 kernel otherwise)", C);
+  MODE_CHECK_ARG(Co >= 64 && Co <= 256 && Co % 64 == 0, "sphere_conv_bf16: Co (%d) must be 64, 128, 192 or 256", Co);
+  ScParams p;
+  p.x = x, p.pos = pos, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.out = out;
+  p.B = B, p.C = C, p.H = H, p.W = W, p.Co = Co, p.relu = relu;
+  p.npix = (long long)B * H * W;
+  MODE_CHECK_ARG((p.npix + 127) / 128 < 2147483647LL, "sphere_conv_bf16: too many tiles");
+  p.ntiles = (int)((p.npix + 127) / 128);
+  const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + (2 * kStagesS + 2) * 8 + 16;
+  static thread_local size_t attr = 0;
+  if (smem > attr) {
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_bf16");
+    attr = smem;
+  }
+  const int grid = std::min(p.ntiles, 2 * kNumSMs);
+  sphere_conv_tc_kernel<<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
+  MODE_CHECK_LAUNCH("sphere_conv_bf16");
+  return MODE_OK;
+}

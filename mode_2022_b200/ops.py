@@ -136,6 +136,45 @@ def _(x, pos, weight, scale, shift, residual, relu):
   return x.new_empty((x.shape[0], weight.shape[0], x.shape[2], x.shape[3]))
 
 
+def sphere_conv_pack_weights(weight: torch.Tensor) -> torch.Tensor:
+  """(Co,C,3,3) fp32 -> bf16 weight slabs [tap][C/64][8][Co][8] streamed by the tensor-core kernel."""
+  weight = _chk(weight, torch.float32, 'sphere_conv_pack_weights')
+  Co, Cc, Kh, Kw = weight.shape
+  if (Kh, Kw) != (3, 3):
+    raise ValueError('sphere_conv_pack_weights: 3x3 kernels only')
+  out = torch.empty(9 * Cc * Co, dtype=torch.bfloat16, device=weight.device)
+  _lib.call('mode_sphere_conv_pack_weights', _p(weight), _p(out), Cc, Co, _stream())
+  return out
+
+
+@torch.library.custom_op('mode_b200::sphere_conv_bf16', mutates_args=())
+def sphere_conv_bf16(x: torch.Tensor, pos: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+                     residual: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+  """NHWC bf16 spherical conv on tcgen05 tensor cores (gather fused into operand staging) + affine + residual + ReLU.
+  x (B,H,W,C) bf16 -> (B,H,W,cout) bf16."""
+  if x.dim() != 4:
+    raise ValueError('Expected 4D tensor as input, got {}D tensor instead.'.format(x.dim()))
+  x = _chk(x, torch.bfloat16, 'sphere_conv_bf16')
+  pos = _chk(pos, torch.float32, 'sphere_conv_bf16')
+  w_packed = _chk(w_packed, torch.bfloat16, 'sphere_conv_bf16')
+  B, H, W, Cc = x.shape
+  if pos.numel() != 18 * H * W:
+    raise RuntimeError(f'invalid spatial size of position, expected 18x{H}x{W}, got {tuple(pos.shape)}')
+  if w_packed.numel() != 9 * Cc * cout:
+    raise RuntimeError('sphere_conv_bf16: packed weight size does not match (C, cout)')
+  out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
+  if residual is not None and residual.shape != out.shape:
+    raise RuntimeError('sphere_conv_bf16: residual shape mismatch')
+  _lib.call('mode_sphere_conv_bf16', _p(x), _p(pos), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
+            _p(_opt(residual, torch.bfloat16, 'residual')), _p(out), B, Cc, H, W, cout, int(relu), _stream())
+  return out
+
+
+@sphere_conv_bf16.register_fake
+def _(x, pos, w_packed, cout, scale, shift, residual, relu):
+  return torch.empty((*x.shape[:3], cout), dtype=torch.bfloat16, device=x.device)
+
+
 # ------------------------------------------------------------------------------------------------
 # a5. conv3d family
 # ------------------------------------------------------------------------------------------------

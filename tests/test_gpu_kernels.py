@@ -258,3 +258,25 @@ def test_conv3d_bf16_classifier_fp32_out(ops):
   got = ops.conv3d_bf16(x.permute(0, 2, 3, 4, 1).contiguous().cuda(), wp, 1, None, None, res.permute(0, 2, 3, 4, 1).contiguous().cuda(), 0, False, True)
   assert got.dtype == torch.float32 and got.shape == (2, 6, 20, 12, 1)
   assert (got.cpu().permute(0, 4, 1, 2, 3) - want).abs().max().item() <= 1e-4
+
+
+# ---------------------------------------------------------------------------- a2 sphere conv on tensor cores (bf16)
+@pytest.mark.parametrize('B,C,Co,h,w,st', [(1, 64, 128, 16, 8, 'Cassini'), (2, 128, 128, 32, 16, 'Cassini'), (1, 128, 128, 16, 32, 'ERP'), (3, 64, 64, 8, 16, 'ERP'),
+                                            (1, 128, 128, 40, 20, 'Cassini')])
+def test_sphere_conv_bf16_tensor_core(ops, B, C, Co, h, w, st):
+  x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 21)
+  xq, wq = x.bfloat16(), wgt.bfloat16()
+  scale, shift = torch.rand(Co) + 0.5, torch.randn(Co)
+  res = torch.randn(B, Co, h, w).bfloat16()
+  want = F.relu(O.sphere_conv(xq.float(), pos, wq.float()) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float())
+  wp = ops.sphere_conv_pack_weights(wgt.cuda())
+  got = ops.sphere_conv_bf16(xq.permute(0, 2, 3, 1).contiguous().cuda(), pos.cuda(), wp, Co, scale.cuda(), shift.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), True)
+  torch.cuda.synchronize()
+  got = got.float().cpu().permute(0, 3, 1, 2)
+  err = (got - want).abs()
+  # the blended sample is rounded to bf16 before the MMA (the A operand is bf16) and the output is bf16: 2^-7 relative
+  tol = 2.0**-6 * want.abs().clamp_min(1.0)
+  assert (err <= tol).all(), (err.max().item(), (err / tol).max().item())
+  plain = ops.sphere_conv_bf16(xq.permute(0, 2, 3, 1).contiguous().cuda(), pos.cuda(), wp, Co, None, None, None, False).float().cpu().permute(0, 3, 1, 2)
+  want_plain = O.sphere_conv(xq.float(), pos, wq.float())
+  assert ((plain - want_plain).abs() <= 2.0**-6 * want_plain.abs().clamp_min(1.0)).all()
