@@ -210,8 +210,8 @@ def run_ours(args):
       by = {}
       for name, _a, e0, e1 in prof:
         by.setdefault(name, []).append(e0.elapsed_time(e1))
-      t_conv = sum(by.get('mode_conv3d_bf16', [])) / 3.0  # ms per step in the conv3d kernels
-      n_conv = len(by.get('mode_conv3d_bf16', [])) // 3
+      t_conv = sum(by.get('mode_conv3d_tc', [])) / 3.0  # ms per step in the conv3d kernels
+      n_conv = len(by.get('mode_conv3d_tc', [])) // 3
       pk = peaks()
       flops = CONV3D_GFLOP_PER_PAIR * 1e9 * PAIRS
       ach = flops / (t_conv * 1e-3) / 1e12 if t_conv > 0 else 0.0
@@ -219,7 +219,7 @@ def run_ours(args):
               'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['bf16_tflops_sustained'], 3), 'traffic': None,
               'peak_source': pk['source'] + ' (sustained bf16; burst %.0f)' % pk['bf16_tflops'], 'launches_per_step': n_conv,
               'ms_per_step_in_kernel': round(t_conv, 3),
-              'other_kernels_ms_per_step': {k: round(sum(v) / 3.0, 3) for k, v in by.items() if k != 'mode_conv3d_bf16'}}
+              'other_kernels_ms_per_step': {k: round(sum(v) / 3.0, 3) for k, v in by.items() if k != 'mode_conv3d_tc'}}
 
   pairs = PAIRS * world * args.steps
   out = {

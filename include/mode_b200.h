@@ -29,7 +29,9 @@ extern "C" {
 #define MODE_ECUDA (-2)    /* CUDA launch / runtime error */
 #define MODE_ENOSUP (-3)   /* configuration not supported by this build */
 
-typedef uint16_t mode_bf16; /* raw bfloat16 bits */
+typedef uint16_t mode_h16; /* raw 16-bit float: bfloat16 (fmt = MODE_FMT_BF16) or IEEE half (fmt = MODE_FMT_FP16) */
+#define MODE_FMT_BF16 0
+#define MODE_FMT_FP16 1
 
 int mode_b200_version(void);
 const char* mode_b200_last_error(void);
@@ -40,10 +42,10 @@ unsigned long long mode_b200_launch_count(void);
  * replaces models/mode_disparity.py:104-113 (CPU zero tensor + H2D + 2*D/4 slice copies).
  *   cost[b,c,i,h,w]    = ref[b,c,h,w]   if w >= i else 0
  *   cost[b,C+c,i,h,w]  = tgt[b,c,h,w-i] if w >= i else 0          i in [0, D4)
- * f32: NCHW in, NCDHW out (bit-exact parity layout).  bf16: NHWC in, NDHWC out (the layout the
- * tensor-core conv3d consumes).  W % 4 == 0 (f32), C % 8 == 0 (bf16). */
+ * f32: NCHW in, NCDHW out (bit-exact parity layout).  16: any 16-bit format, NHWC in, NDHWC out (the layout the
+ * tensor-core conv3d consumes).  W % 4 == 0 (f32), C % 8 == 0 (16). */
 int mode_cost_volume_f32(const float* ref, const float* tgt, float* cost, int B, int C, int H, int W, int D4, void* stream);
-int mode_cost_volume_bf16(const mode_bf16* ref, const mode_bf16* tgt, mode_bf16* cost, int B, int C, int H, int W, int D4, void* stream);
+int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mode_h16* cost, int B, int C, int H, int W, int D4, void* stream);
 
 /* ---- a6/a7. trilinear upsample + softmax + soft-argmin (+ confidence) --------------------------
  * replaces models/mode_disparity.py:143-152 (+131-141 for the training heads), :157-183 and
@@ -61,11 +63,11 @@ int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4
  * scale/shift/residual may be NULL. */
 int mode_sphere_conv_f32(const float* x, const float* pos, const float* w, const float* scale, const float* shift,
                          const float* residual, float* out, int B, int C, int H, int W, int Co, int Kh, int Kw, int relu, void* stream);
-/* bf16 tensor-core variant: x (B,H,W,C) NHWC bf16, w_packed from mode_sphere_conv_pack_weights,
- * out (B,H,W,Co) bf16.  C in {64,128}, Co = 128, 3x3. */
-int mode_sphere_conv_bf16(const mode_bf16* x, const float* pos, const mode_bf16* w_packed, const float* scale, const float* shift,
-                          const mode_bf16* residual, mode_bf16* out, int B, int C, int H, int W, int Co, int relu, void* stream);
-int mode_sphere_conv_pack_weights(const float* w /*Co,C,3,3*/, mode_bf16* w_packed, int C, int Co, void* stream);
+/* tensor-core (tcgen05) variant: x (B,H,W,C) NHWC 16-bit, w_packed from mode_sphere_conv_pack_weights,
+ * out (B,H,W,Co) 16-bit, fp32 accumulation.  C % 64 == 0, Co in {64,128,192,256}, 3x3. */
+int mode_sphere_conv_tc(const mode_h16* x, const float* pos, const mode_h16* w_packed, const float* scale, const float* shift,
+                        const mode_h16* residual, mode_h16* out, int B, int C, int H, int W, int Co, int relu, int fmt, void* stream);
+int mode_sphere_conv_pack_weights(const float* w /*Co,C,3,3*/, mode_h16* w_packed, int C, int Co, int fmt, void* stream);
 
 /* ---- a5. 3-D regularisation convolutions --------------------------------------------------------
  * replace nn.Conv3d / nn.ConvTranspose3d + BatchNorm3d(eval) + residual + ReLU
@@ -75,19 +77,20 @@ int mode_sphere_conv_pack_weights(const float* w /*Co,C,3,3*/, mode_bf16* w_pack
  * f32: NCDHW, w in the PyTorch layout ((Co,Ci,3,3,3); transposed: (Ci,Co,3,3,3)).  Di/Hi/Wi are INPUT dims. */
 int mode_conv3d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* out,
                     int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu, void* stream);
-/* bf16 tensor-core (tcgen05) variant: NDHWC bf16 activations, weights pre-packed per tap.
- * out_f32 != NULL writes fp32 (B,Do,Ho,Wo,CoReal) instead of bf16 (used by the 32->1 classifier). */
-int mode_conv3d_pack_weights(const float* w, mode_bf16* w_packed, int Ci, int Co, int CoPad, int mode, void* stream);
-int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, const float* scale, const float* shift, const mode_bf16* residual,
-                     const float* residual_f32, mode_bf16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu,
-                     void* stream);
+/* tensor-core (tcgen05) variant: NDHWC 16-bit activations (fmt), weights pre-packed per tap, fp32 accumulation in TMEM.
+ * out_f32 != NULL writes fp32 (B,Do,Ho,Wo,Co) instead of 16-bit (used by the 32->1 classifier, Co <= 16).
+ * Ci in {32,64}; Co % 32 == 0 for 16-bit output. */
+int mode_conv3d_pack_weights(const float* w, mode_h16* w_packed, int Ci, int Co, int mode, int fmt, void* stream);
+int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const float* scale, const float* shift, const mode_h16* residual,
+                   const float* residual_f32, mode_h16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu,
+                   int fmt, void* stream);
 size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode);
 /* profiling aid: when set (device pointer to >= 8*grid int64), every conv3d_bf16 launch records per-CTA {smid, start ns, end ns, items} */
 int mode_conv3d_set_debug_buffer(void* dev_ptr);
 
-/* ---- layout helpers (NCHW fp32 <-> NHWC bf16), used at the cuDNN / custom-kernel seams ----------- */
-int mode_nchw_f32_to_nhwc_bf16(const float* x, mode_bf16* y, int B, int C, int HW, void* stream);
-int mode_nhwc_bf16_to_nchw_f32(const mode_bf16* x, float* y, int B, int C, int HW, void* stream);
+/* ---- layout helpers (NCHW fp32 <-> NHWC 16-bit), used at the cuDNN / custom-kernel seams ---------- */
+int mode_nchw_f32_to_nhwc_16(const float* x, mode_h16* y, int B, int C, int HW, int fmt, void* stream);
+int mode_nhwc_16_to_nchw_f32(const mode_h16* x, float* y, int B, int C, int HW, int fmt, void* stream);
 
 /* ---- a8. disparity -> depth ----------------------------------------------------------------------
  * replaces disp2depth's triangulation, save_output_disparity_stage.py:118-133 (fp64 arithmetic on fp32 inputs,

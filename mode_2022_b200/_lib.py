@@ -17,16 +17,16 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 # name -> argtypes; every function returns int status (see include/mode_b200.h)
 SIGNATURES = {
     'mode_cost_volume_f32': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    'mode_cost_volume_bf16': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'mode_cost_volume_16': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'mode_disp_regress': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    'mode_sphere_conv_bf16': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _vp],
+    'mode_sphere_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _i, _vp],
     'mode_conv3d_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_conv3d_pack_weights': [_vp, _vp, _i, _i, _i, _i, _vp],
-    'mode_conv3d_bf16': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    'mode_nchw_f32_to_nhwc_bf16': [_vp, _vp, _i, _i, _i, _vp],
-    'mode_nhwc_bf16_to_nchw_f32': [_vp, _vp, _i, _i, _i, _vp],
+    'mode_conv3d_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_nchw_f32_to_nhwc_16': [_vp, _vp, _i, _i, _i, _i, _vp],
+    'mode_nhwc_16_to_nchw_f32': [_vp, _vp, _i, _i, _i, _i, _vp],
     'mode_disp_to_depth': [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],

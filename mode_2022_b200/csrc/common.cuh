@@ -2,6 +2,7 @@
 #pragma once
 #include <algorithm>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -57,6 +58,34 @@ __device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 16-bit storage formats of the tensor-core path: bf16 (BASELINE's named dtype) or fp16 (same speed, 3 more mantissa bits)
+constexpr int kFmtBF16 = 0, kFmtFP16 = 1;
+template <int FMT>
+__device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
+  if (FMT == kFmtBF16) {
+    lo = __uint_as_float(v << 16);
+    hi = __uint_as_float(v & 0xFFFF0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    lo = f.x, hi = f.y;
+  }
+}
+template <int FMT>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (FMT == kFmtBF16) return pack_bf16x2(lo, hi);
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint16_t float_to_h16_bits(float f, int fmt) {
+  if (fmt == kFmtBF16) return float_to_bf16_bits(f);
+  const __half h = __float2half_rn(f);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+__device__ __forceinline__ float h16_bits_to_float(uint16_t b, int fmt) {
+  if (fmt == kFmtBF16) return bf16_bits_to_float(b);
+  return __half2float(*reinterpret_cast<const __half*>(&b));
 }
 
 // streaming 128-bit accesses: data touched once should not pollute L1

@@ -184,8 +184,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          (1ull << 46);  // descriptor version 1 (Blackwell); base_offset 0, layout_type 0 = SWIZZLE_NONE
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = NT
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int fmt = 0) {
+  return (1u << 4) | ((fmt == 0 ? 1u : 0u) << 7) | ((fmt == 0 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 struct Item {
@@ -247,7 +247,7 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
 //   mode 1: odd input planes feed kd = 2 (block 0) and kd = 0 (block 1); even planes feed kd = 1 (block 2)
 __host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
 
-template <int MODE, int NT>
+template <int MODE, int NT, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p) {
   using G = Geo<MODE>;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
               oa = ob = rel2 >> 1, wb_a = 2;
             }
           }
-          const uint32_t i1 = make_idesc((ob - oa + 1) * NT);
+          const uint32_t i1 = make_idesc((ob - oa + 1) * NT, FMT);
           const uint32_t d1 = tmem_base + (uint32_t)oa * NT;
           long long c0 = p.dbg ? clock64() : 0;
           for (; next_new <= ob; ++next_new) {  // first touch of a block: the epilogue must have drained + zeroed it
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
             mbar_wait(smem_u32(full_bar + slot), phase);
             tc_fence_after();
             const uint32_t a0 = desc_lo(smem_u32(slots_s + (size_t)slot * kSlotBytes), kChunkStride);
-            constexpr uint32_t idesc = make_idesc(NT);
+            constexpr uint32_t idesc = make_idesc(NT, FMT);
 #pragma unroll 1
             for (int kd = 0; kd < 3; ++kd) {  // oldest output plane first
               const int od = 2 * pl - 1 + kd;
@@ -593,8 +593,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
                   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    y[2 * j] += __uint_as_float(rr[j] << 16);
-                    y[2 * j + 1] += __uint_as_float(rr[j] & 0xFFFF0000u);
+                    float r0, r1;
+                    unpack2<FMT>(rr[j], r0, r1);
+                    y[2 * j] += r0, y[2 * j + 1] += r1;
                   }
                 }
                 if (p.relu) {
@@ -602,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
                   for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
                 uint4 o;
-                o.x = pack_bf16x2(y[0], y[1]), o.y = pack_bf16x2(y[2], y[3]), o.z = pack_bf16x2(y[4], y[5]), o.w = pack_bf16x2(y[6], y[7]);
+                o.x = pack2<FMT>(y[0], y[1]), o.y = pack2<FMT>(y[2], y[3]), o.z = pack2<FMT>(y[4], y[5]), o.w = pack2<FMT>(y[6], y[7]);
                 *reinterpret_cast<uint4*>(op + q * 8) = o;
               }
             }
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
 }
 
 // weights (Co,Ci,3,3,3) [mode 0/1] or (Ci,Co,3,3,3) [mode 2], fp32 -> [nblk][khalf][27][4][NT][8] bf16, zero padded
-__global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Ci, int Co, int NT, int nblk, int mode,
+__global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int Ci, int Co, int NT, int nblk, int mode, int fmt,
                                 long long total) {
   // mode 2:   [nblk][khalf][tap 27][kc 4][NT][8]
   // mode 0/1: [nblk][khalf][tap 9 (kh,kw)][kc 4][depth block 3][NT][8]   (see wblock_of_kd)
@@ -671,22 +672,26 @@ __global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restric
     const int co = nb * NT + n, ci = kh * kStageCh + kc * 8 + j, t = kd * 9 + t9;
     float v = 0.f;
     if (co < Co) v = (mode == 2) ? w[((size_t)ci * Co + co) * 27 + t] : w[((size_t)co * Ci + ci) * 27 + t];
-    wp[e] = float_to_bf16_bits(v);
+    wp[e] = float_to_h16_bits(v, fmt);
   }
 }
 
 int pick_nt(int Co) { return Co >= 32 ? 32 : 16; }
 
-template <int MODE, int NT>
-int launch_tc(const TcParams& p, int grid, size_t smem, cudaStream_t s) {
+template <int MODE, int NT, int FMT>
+int launch_tc2(const TcParams& p, int grid, size_t smem, cudaStream_t s) {
   static thread_local size_t attr = 0;
   if (smem > attr) {
-    MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_bf16");
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
     attr = smem;
   }
-  conv3d_tc_kernel<MODE, NT><<<grid, kThreads, smem, s>>>(p);
-  MODE_CHECK_LAUNCH("conv3d_bf16");
+  conv3d_tc_kernel<MODE, NT, FMT><<<grid, kThreads, smem, s>>>(p);
+  MODE_CHECK_LAUNCH("conv3d_tc");
   return MODE_OK;
+}
+template <int MODE, int NT>
+int launch_tc(const TcParams& p, int fmt, int grid, size_t smem, cudaStream_t s) {
+  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, grid, smem, s);
 }
 
 }  // namespace
@@ -705,28 +710,29 @@ extern "C" size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode) {
   return (size_t)nblk * (Ci / kStageCh) * 27 * 4 * NT * 8;
 }
 
-extern "C" int mode_conv3d_pack_weights(const float* w, mode_bf16* w_packed, int Ci, int Co, int CoPad, int mode, void* stream) {
+extern "C" int mode_conv3d_pack_weights(const float* w, mode_h16* w_packed, int Ci, int Co, int mode, int fmt, void* stream) {
   MODE_CHECK_ARG(w && w_packed, "conv3d_pack_weights: null pointer");
   MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_pack_weights: Ci must be 32 or 64 (got %d)", Ci);
   MODE_CHECK_ARG(Co >= 1 && mode >= 0 && mode <= 2, "conv3d_pack_weights: bad Co/mode");
-  (void)CoPad;
+  MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "conv3d_pack_weights: fmt must be 0 (bf16) or 1 (fp16)");
   const int NT = pick_nt(Co);
   const int nblk = (Co + NT - 1) / NT;
   const long long total = (long long)mode_conv3d_packed_weight_elems(Ci, Co, mode);
-  pack_w3d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, Ci, Co, NT, nblk, mode, total);
+  pack_w3d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, Ci, Co, NT, nblk, mode, fmt, total);
   MODE_CHECK_LAUNCH("conv3d_pack_weights");
   return MODE_OK;
 }
 
-extern "C" int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, const float* scale, const float* shift, const mode_bf16* residual,
-                                const float* residual_f32, mode_bf16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode,
-                                int relu, void* stream) {
-  MODE_CHECK_ARG(x && w_packed && (out || out_f32), "conv3d_bf16: null pointer");
-  MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_bf16: Ci must be 32 or 64 (got %d)", Ci);
-  MODE_CHECK_ARG(B > 0 && Di > 0 && Hi > 0 && Wi > 0 && mode >= 0 && mode <= 2, "conv3d_bf16: bad shape/mode");
+extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const float* scale, const float* shift, const mode_h16* residual,
+                              const float* residual_f32, mode_h16* out, float* out_f32, int B, int Ci, int Co, int Di, int Hi, int Wi, int mode,
+                              int relu, int fmt, void* stream) {
+  MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "conv3d_tc: fmt must be 0 (bf16) or 1 (fp16)");
+  MODE_CHECK_ARG(x && w_packed && (out || out_f32), "conv3d_tc: null pointer");
+  MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_tc: Ci must be 32 or 64 (got %d)", Ci);
+  MODE_CHECK_ARG(B > 0 && Di > 0 && Hi > 0 && Wi > 0 && mode >= 0 && mode <= 2, "conv3d_tc: bad shape/mode");
   const int NT = pick_nt(Co);
-  MODE_CHECK_ARG(out_f32 ? (Co <= 16) : (Co % 32 == 0), "conv3d_bf16: Co=%d unsupported (bf16 out needs Co %% 32 == 0, fp32 out needs Co <= 16)", Co);
-  MODE_CHECK_ARG(!(mode == 2 && NT != 32), "conv3d_bf16: transposed conv needs Co %% 32 == 0");
+  MODE_CHECK_ARG(out_f32 ? (Co <= 16) : (Co % 32 == 0), "conv3d_tc: Co=%d unsupported (bf16 out needs Co %% 32 == 0, fp32 out needs Co <= 16)", Co);
+  MODE_CHECK_ARG(!(mode == 2 && NT != 32), "conv3d_tc: transposed conv needs Co %% 32 == 0");
   TcParams p;
   p.x = x, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.res_f32 = residual_f32, p.out = out, p.out_f32 = out_f32;
   p.dbg = g_tc_dbg;
@@ -748,7 +754,7 @@ extern "C" int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, c
   const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128;
   const size_t budget = 227 * 1024;
   int nslots = (int)std::min<size_t>(kMaxSlots, (budget - w_bytes - misc) / slot_bytes);
-  MODE_CHECK_ARG(nslots >= 2, "conv3d_bf16: not enough shared memory for a 2-stage pipeline");
+  MODE_CHECK_ARG(nslots >= 2, "conv3d_tc: not enough shared memory for a 2-stage pipeline");
   p.nslots = nslots;
   // depth chunking: split the depth range into nch BALANCED chunks (chunk = ceil(d / nch)); pick the nch that minimises
   // the critical-path stage count  rounds x (chunk + halo)  (persistent CTAs, round-robin items).
@@ -771,19 +777,19 @@ extern "C" int mode_conv3d_bf16(const mode_bf16* x, const mode_bf16* w_packed, c
   p.chunk = best_chunk;
   p.nchunks = ceil_div(d_dim, p.chunk);
   const long long per_nb = cols * p.nchunks;
-  MODE_CHECK_ARG(per_nb * p.nblk < 2147483647LL, "conv3d_bf16: too many work items");
+  MODE_CHECK_ARG(per_nb * p.nblk < 2147483647LL, "conv3d_tc: too many work items");
   p.total_items = (int)(per_nb * p.nblk);
   const int ctas_per_nb = (int)std::min<long long>(per_nb, kNumSMs / p.nblk);
   const int grid = ctas_per_nb * p.nblk;
   const size_t smem = w_bytes + (size_t)nslots * slot_bytes + misc;
   cudaStream_t s = (cudaStream_t)stream;
   if (NT == 32) {
-    if (mode == 0) return launch_tc<0, 32>(p, grid, smem, s);
-    if (mode == 1) return launch_tc<1, 32>(p, grid, smem, s);
-    return launch_tc<2, 32>(p, grid, smem, s);
+    if (mode == 0) return launch_tc<0, 32>(p, fmt, grid, smem, s);
+    if (mode == 1) return launch_tc<1, 32>(p, fmt, grid, smem, s);
+    return launch_tc<2, 32>(p, fmt, grid, smem, s);
   }
-  if (mode == 0) return launch_tc<0, 16>(p, grid, smem, s);
-  if (mode == 1) return launch_tc<1, 16>(p, grid, smem, s);
-  set_error("conv3d_bf16: unsupported configuration");
+  if (mode == 0) return launch_tc<0, 16>(p, fmt, grid, smem, s);
+  if (mode == 1) return launch_tc<1, 16>(p, fmt, grid, smem, s);
+  set_error("conv3d_tc: unsupported configuration");
   return MODE_ENOSUP;
 }

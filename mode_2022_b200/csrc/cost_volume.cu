@@ -73,14 +73,14 @@ extern "C" int mode_cost_volume_f32(const float* ref, const float* tgt, float* c
   return MODE_OK;
 }
 
-extern "C" int mode_cost_volume_bf16(const mode_bf16* ref, const mode_bf16* tgt, mode_bf16* cost, int B, int C, int H, int W, int D4,
+extern "C" int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mode_h16* cost, int B, int C, int H, int W, int D4,
                                      void* stream) {
-  MODE_CHECK_ARG(ref && tgt && cost, "cost_volume_bf16: null pointer");
-  MODE_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && D4 > 0, "cost_volume_bf16: bad shape B=%d C=%d H=%d W=%d D4=%d", B, C, H, W, D4);
-  MODE_CHECK_ARG(C % 8 == 0, "cost_volume_bf16: C (%d) must be a multiple of 8", C);
+  MODE_CHECK_ARG(ref && tgt && cost, "cost_volume_16: null pointer");
+  MODE_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && D4 > 0, "cost_volume_16: bad shape B=%d C=%d H=%d W=%d D4=%d", B, C, H, W, D4);
+  MODE_CHECK_ARG(C % 8 == 0, "cost_volume_16: C (%d) must be a multiple of 8", C);
   long long total8 = (long long)B * D4 * H * W * (2 * C / 8);
   int blocks = (int)std::min<long long>((total8 + 255) / 256, (long long)kNumSMs * 32);
   cost_volume_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, tgt, cost, C, H, W, D4, total8);
-  MODE_CHECK_LAUNCH("cost_volume_bf16");
+  MODE_CHECK_LAUNCH("cost_volume_16");
   return MODE_OK;
 }

@@ -87,8 +87,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14); }
-__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+__host__ __device__ constexpr uint32_t make_idesc(int n, int fmt) { return (1u << 4) | ((fmt == 0 ? 1u : 0u) << 7) | ((fmt == 0 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
 
+template <int FMT>
 __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -180,11 +181,11 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
             uint32_t o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float lo = (w1[j] * __uint_as_float(a1[q] << 16) + w2[j] * __uint_as_float(a2[q] << 16) + w3[j] * __uint_as_float(a3[q] << 16) +
-                                w4[j] * __uint_as_float(a4[q] << 16));
-              const float hi = (w1[j] * __uint_as_float(a1[q] & 0xFFFF0000u) + w2[j] * __uint_as_float(a2[q] & 0xFFFF0000u) +
-                                w3[j] * __uint_as_float(a3[q] & 0xFFFF0000u) + w4[j] * __uint_as_float(a4[q] & 0xFFFF0000u));
-              o[q] = pack_bf16x2(lo, hi);
+              float l1, h1, l2, h2, l3, h3, l4, h4;
+              unpack2<FMT>(a1[q], l1, h1), unpack2<FMT>(a2[q], l2, h2), unpack2<FMT>(a3[q], l3, h3), unpack2<FMT>(a4[q], l4, h4);
+              const float lo = (w1[j] * l1 + w2[j] * l2 + w3[j] * l3 + w4[j] * l4);
+              const float hi = (w1[j] * h1 + w2[j] * h2 + w3[j] * h3 + w4[j] * h4);
+              o[q] = pack2<FMT>(lo, hi);
             }
             const int pix_l = (tid >> 3) + 32 * j;
             *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -224,13 +225,17 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
               const uint4 r = ld_nc_v4(rp + g * 8);
               const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) y[2 * e] += __uint_as_float(rr[e] << 16), y[2 * e + 1] += __uint_as_float(rr[e] & 0xFFFF0000u);
+              for (int e = 0; e < 4; ++e) {
+                float r0, r1;
+                unpack2<FMT>(rr[e], r0, r1);
+                y[2 * e] += r0, y[2 * e + 1] += r1;
+              }
             }
             if (p.relu) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
             }
-            *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
           }
         }
       }
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
     }
   } else {
     // =================================================== MMA issuer (warp-uniform control flow, one elected lane issues)
-    const uint32_t idesc = make_idesc(p.Co);
+    const uint32_t idesc = make_idesc(p.Co, FMT);
     const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
     uint32_t stage = 0, tile_n = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_n) {
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
 }
 
 // (Co, C, 3, 3) fp32 -> [tap 9][half C/64][chunk 8][n Co][8] bf16
-__global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int C, int Co, long long total) {
+__global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int C, int Co, int fmt, long long total) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     long long r = e;
     const int j = (int)(r % 8);
@@ -281,41 +286,46 @@ __global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __res
     const int half = (int)(r % (C / 64));
     const int k = (int)(r / (C / 64));
     const int c = half * 64 + kc * 8 + j;
-    wp[e] = float_to_bf16_bits(w[((size_t)n * C + c) * 9 + k]);
+    wp[e] = float_to_h16_bits(w[((size_t)n * C + c) * 9 + k], fmt);
   }
 }
 
 }  // namespace
 
-extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_bf16* w_packed, int C, int Co, void* stream) {
+extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_h16* w_packed, int C, int Co, int fmt, void* stream) {
   MODE_CHECK_ARG(w && w_packed, "sphere_conv_pack_weights: null pointer");
   MODE_CHECK_ARG(C > 0 && C % 64 == 0 && Co >= 16 && Co <= 256 && Co % 16 == 0, "sphere_conv_pack_weights: need C %% 64 == 0 and Co %% 16 == 0, Co <= 256");
   const long long total = 9LL * C * Co;
-  pack_wsphere_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, C, Co, total);
+  pack_wsphere_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, C, Co, fmt, total);
   MODE_CHECK_LAUNCH("sphere_conv_pack_weights");
   return MODE_OK;
 }
 
-extern "C" int mode_sphere_conv_bf16(const mode_bf16* x, const float* pos, const mode_bf16* w_packed, const float* scale, const float* shift,
-                                     const mode_bf16* residual, mode_bf16* out, int B, int C, int H, int W, int Co, int relu, void* stream) {
-  MODE_CHECK_ARG(x && pos && w_packed && out, "sphere_conv_bf16: null pointer");
-  MODE_CHECK_ARG(B > 0 && H > 0 && W > 0, "sphere_conv_bf16: bad shape");
-  MODE_CHECK_ARG(C > 0 && C % 64 == 0, "sphere_conv_bf16: C (%d) must be a multiple of 64 (use the f32 kernel otherwise)", C);
-  MODE_CHECK_ARG(Co >= 64 && Co <= 256 && Co % 64 == 0, "sphere_conv_bf16: Co (%d) must be 64, 128, 192 or 256", Co);
+extern "C" int mode_sphere_conv_tc(const mode_h16* x, const float* pos, const mode_h16* w_packed, const float* scale, const float* shift,
+                                   const mode_h16* residual, mode_h16* out, int B, int C, int H, int W, int Co, int relu, int fmt, void* stream) {
+  MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "sphere_conv_tc: fmt must be 0 (bf16) or 1 (fp16)");
+  MODE_CHECK_ARG(x && pos && w_packed && out, "sphere_conv_tc: null pointer");
+  MODE_CHECK_ARG(B > 0 && H > 0 && W > 0, "sphere_conv_tc: bad shape");
+  MODE_CHECK_ARG(C > 0 && C % 64 == 0, "sphere_conv_tc: C (%d) must be a multiple of 64 (use the f32 kernel otherwise)", C);
+  MODE_CHECK_ARG(Co >= 64 && Co <= 256 && Co % 64 == 0, "sphere_conv_tc: Co (%d) must be 64, 128, 192 or 256", Co);
   ScParams p;
   p.x = x, p.pos = pos, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.out = out;
   p.B = B, p.C = C, p.H = H, p.W = W, p.Co = Co, p.relu = relu;
   p.npix = (long long)B * H * W;
-  MODE_CHECK_ARG((p.npix + 127) / 128 < 2147483647LL, "sphere_conv_bf16: too many tiles");
+  MODE_CHECK_ARG((p.npix + 127) / 128 < 2147483647LL, "sphere_conv_tc: too many tiles");
   p.ntiles = (int)((p.npix + 127) / 128);
   const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + (2 * kStagesS + 2) * 8 + 16;
   static thread_local size_t attr = 0;
   if (smem > attr) {
-    MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_bf16");
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
     attr = smem;
   }
   const int grid = std::min(p.ntiles, 2 * kNumSMs);
-  sphere_conv_tc_kernel<<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
-  MODE_CHECK_LAUNCH("sphere_conv_bf16");
+  if (fmt == kFmtBF16)
+    sphere_conv_tc_kernel<kFmtBF16><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
+  else
+    sphere_conv_tc_kernel<kFmtFP16><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
+  MODE_CHECK_LAUNCH("sphere_conv_tc");
   return MODE_OK;
 }

@@ -6,9 +6,10 @@ output shapes and state-dict keys), executing the stereo hot path on libmode_b20
   3-D regularisation   mode_conv3d_* with BN/residual/ReLU fused            (a5, reference :11-46,:115-129)
   regression + conf    mode_disp_regress                                    (a6/a7, reference :143-183)
 
-`precision='fp32'` is the parity mode (NCHW/NCDHW fp32 everywhere, CUDA-core kernels, <=1e-4 relative on the
-disparity); `precision='bf16'` is the throughput mode (NHWC/NDHWC bf16 activations, tcgen05 tensor-core
-kernels with fp32 accumulation and fp32 logits/regression).  Left and right images share the feature
+`precision='fp32'` is the parity mode (NCHW/NCDHW fp32 everywhere, CUDA-core kernels); `precision='bf16'` is the
+throughput mode BASELINE.json names (NHWC/NDHWC bf16 activations, tcgen05 tensor-core kernels with fp32 accumulation
+and fp32 logits/regression); `precision='fp16'` runs the same kernels at the same speed with fp16 storage (3 more
+mantissa bits: 8x less rounding noise per stored activation).  Left and right images share the feature
 extractor, so they are run as one batch of 2B.
 
 Only inference is implemented in this round (the backward kernels are SURVEY.md §8f row 1): calling the
@@ -48,8 +49,8 @@ class ModeDisparity(nn.Module):
     self.out_conf = out_conf
     self.sphereType = sphereType
     self.precision = precision or os.environ.get('MODE_B200_PRECISION', 'bf16')
-    if self.precision not in ('fp32', 'bf16'):
-      raise ValueError("precision must be 'fp32' or 'bf16'")
+    if self.precision not in ('fp32', 'bf16', 'fp16'):
+      raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
     if conv == 'Regular':
       from .psm_features import feature_extraction
       self.feature_extraction = feature_extraction()

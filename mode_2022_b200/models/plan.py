@@ -124,5 +124,6 @@ class Fp32Plan(_PlanBase):
 def build_plan(model):
   if model.precision == 'fp32':
     return Fp32Plan(model)
+  import torch
   from .plan_bf16 import Bf16Plan
-  return Bf16Plan(model)
+  return Bf16Plan(model, torch.float16 if model.precision == 'fp16' else torch.bfloat16)

@@ -40,6 +40,18 @@ def _opt(t: Optional[torch.Tensor], dtype, name: str):
   return None if t is None else _chk(t, dtype, name)
 
 
+HALF_DTYPES = (torch.bfloat16, torch.float16)
+
+
+def _fmt(dtype) -> int:
+  """MODE_FMT_* code of a 16-bit storage dtype (include/mode_b200.h)."""
+  if dtype == torch.bfloat16:
+    return 0
+  if dtype == torch.float16:
+    return 1
+  raise TypeError(f'expected torch.bfloat16 or torch.float16, got {dtype}')
+
+
 # ------------------------------------------------------------------------------------------------
 # a4. cost volume
 # ------------------------------------------------------------------------------------------------
@@ -48,7 +60,7 @@ def _opt(t: Optional[torch.Tensor], dtype, name: str):
 @torch.library.custom_op('mode_b200::cost_volume', mutates_args=())
 def cost_volume(ref: torch.Tensor, tgt: torch.Tensor, d4: int) -> torch.Tensor:
   """fp32: (B,C,H,W) x2 -> (B,2C,D4,H,W)   [reference layout, models/mode_disparity.py:104-113]
-  bf16: (B,H,W,C) x2 -> (B,D4,H,W,2C)   [NDHWC, consumed by the tensor-core conv3d]"""
+  bf16/fp16: (B,H,W,C) x2 -> (B,D4,H,W,2C)   [NDHWC, consumed by the tensor-core conv3d]"""
   if ref.shape != tgt.shape or ref.dim() != 4:
     raise ValueError('cost_volume: ref/tgt must be 4-D tensors of equal shape')
   if ref.dtype == torch.float32:
@@ -57,10 +69,11 @@ def cost_volume(ref: torch.Tensor, tgt: torch.Tensor, d4: int) -> torch.Tensor:
     out = ref.new_empty((B, 2 * Cc, d4, H, W))
     _lib.call('mode_cost_volume_f32', _p(ref), _p(tgt), _p(out), B, Cc, H, W, d4, _stream())
   else:
-    ref, tgt = _chk(ref, torch.bfloat16, 'cost_volume'), _chk(tgt, torch.bfloat16, 'cost_volume')
+    _fmt(ref.dtype)
+    ref, tgt = _chk(ref, ref.dtype, 'cost_volume'), _chk(tgt, ref.dtype, 'cost_volume')
     B, H, W, Cc = ref.shape
     out = ref.new_empty((B, d4, H, W, 2 * Cc))
-    _lib.call('mode_cost_volume_bf16', _p(ref), _p(tgt), _p(out), B, Cc, H, W, d4, _stream())
+    _lib.call('mode_cost_volume_16', _p(ref), _p(tgt), _p(out), B, Cc, H, W, d4, _stream())
   return out
 
 
@@ -136,43 +149,44 @@ def _(x, pos, weight, scale, shift, residual, relu):
   return x.new_empty((x.shape[0], weight.shape[0], x.shape[2], x.shape[3]))
 
 
-def sphere_conv_pack_weights(weight: torch.Tensor) -> torch.Tensor:
-  """(Co,C,3,3) fp32 -> bf16 weight slabs [tap][C/64][8][Co][8] streamed by the tensor-core kernel."""
+def sphere_conv_pack_weights(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+  """(Co,C,3,3) fp32 -> 16-bit weight slabs [tap][C/64][8][Co][8] streamed by the tensor-core kernel."""
   weight = _chk(weight, torch.float32, 'sphere_conv_pack_weights')
   Co, Cc, Kh, Kw = weight.shape
   if (Kh, Kw) != (3, 3):
     raise ValueError('sphere_conv_pack_weights: 3x3 kernels only')
-  out = torch.empty(9 * Cc * Co, dtype=torch.bfloat16, device=weight.device)
-  _lib.call('mode_sphere_conv_pack_weights', _p(weight), _p(out), Cc, Co, _stream())
+  out = torch.empty(9 * Cc * Co, dtype=dtype, device=weight.device)
+  _lib.call('mode_sphere_conv_pack_weights', _p(weight), _p(out), Cc, Co, _fmt(dtype), _stream())
   return out
 
 
 @torch.library.custom_op('mode_b200::sphere_conv_bf16', mutates_args=())
 def sphere_conv_bf16(x: torch.Tensor, pos: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                      residual: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
-  """NHWC bf16 spherical conv on tcgen05 tensor cores (gather fused into operand staging) + affine + residual + ReLU.
-  x (B,H,W,C) bf16 -> (B,H,W,cout) bf16."""
+  """NHWC bf16/fp16 spherical conv on tcgen05 tensor cores (gather fused into operand staging) + affine + residual
+  + ReLU.  x (B,H,W,C) -> (B,H,W,cout), same 16-bit dtype."""
   if x.dim() != 4:
     raise ValueError('Expected 4D tensor as input, got {}D tensor instead.'.format(x.dim()))
-  x = _chk(x, torch.bfloat16, 'sphere_conv_bf16')
+  fmt = _fmt(x.dtype)
+  x = _chk(x, x.dtype, 'sphere_conv_bf16')
   pos = _chk(pos, torch.float32, 'sphere_conv_bf16')
-  w_packed = _chk(w_packed, torch.bfloat16, 'sphere_conv_bf16')
+  w_packed = _chk(w_packed, x.dtype, 'sphere_conv_bf16')
   B, H, W, Cc = x.shape
   if pos.numel() != 18 * H * W:
     raise RuntimeError(f'invalid spatial size of position, expected 18x{H}x{W}, got {tuple(pos.shape)}')
   if w_packed.numel() != 9 * Cc * cout:
     raise RuntimeError('sphere_conv_bf16: packed weight size does not match (C, cout)')
-  out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
+  out = torch.empty((B, H, W, cout), dtype=x.dtype, device=x.device)
   if residual is not None and residual.shape != out.shape:
     raise RuntimeError('sphere_conv_bf16: residual shape mismatch')
-  _lib.call('mode_sphere_conv_bf16', _p(x), _p(pos), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
-            _p(_opt(residual, torch.bfloat16, 'residual')), _p(out), B, Cc, H, W, cout, int(relu), _stream())
+  _lib.call('mode_sphere_conv_tc', _p(x), _p(pos), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
+            _p(_opt(residual, x.dtype, 'residual')), _p(out), B, Cc, H, W, cout, int(relu), fmt, _stream())
   return out
 
 
 @sphere_conv_bf16.register_fake
 def _(x, pos, w_packed, cout, scale, shift, residual, relu):
-  return torch.empty((*x.shape[:3], cout), dtype=torch.bfloat16, device=x.device)
+  return torch.empty((*x.shape[:3], cout), dtype=x.dtype, device=x.device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -219,42 +233,43 @@ def _(x, weight, scale, shift, residual, mode, relu):
   return x.new_empty((B, Co, *conv3d_out_dims(D, H, W, mode)))
 
 
-def conv3d_pack_weights(weight: torch.Tensor, mode: int) -> torch.Tensor:
-  """fp32 PyTorch-layout 3x3x3 weights -> per-tap bf16 tiles resident in shared memory ([nblk][khalf][27][4][NT][8])."""
+def conv3d_pack_weights(weight: torch.Tensor, mode: int, dtype=torch.bfloat16) -> torch.Tensor:
+  """fp32 PyTorch-layout 3x3x3 weights -> per-tap 16-bit tiles resident in shared memory."""
   weight = _chk(weight, torch.float32, 'conv3d_pack_weights')
   Ci, Co = (weight.shape[0], weight.shape[1]) if mode == DECONV_S2 else (weight.shape[1], weight.shape[0])
   n = _lib.load().mode_conv3d_packed_weight_elems(Ci, Co, mode)
-  out = torch.empty(n, dtype=torch.bfloat16, device=weight.device)
-  _lib.call('mode_conv3d_pack_weights', _p(weight), _p(out), Ci, Co, 0, mode, _stream())
+  out = torch.empty(n, dtype=dtype, device=weight.device)
+  _lib.call('mode_conv3d_pack_weights', _p(weight), _p(out), Ci, Co, mode, _fmt(dtype), _stream())
   return out
 
 
 @torch.library.custom_op('mode_b200::conv3d_bf16', mutates_args=())
 def conv3d_bf16(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                 residual: Optional[torch.Tensor], mode: int, relu: bool, out_f32: bool) -> torch.Tensor:
-  """NDHWC bf16 3x3x3 conv / strided conv / transposed conv on tcgen05 tensor cores with fused affine + residual
-  + ReLU.  x (B,D,H,W,Ci) bf16 -> (B,Do,Ho,Wo,cout) bf16; with out_f32 (cout <= 16, the 32->1 classifier) the
-  output and the residual are fp32."""
-  x = _chk(x, torch.bfloat16, 'conv3d_bf16')
-  w_packed = _chk(w_packed, torch.bfloat16, 'conv3d_bf16')
+  """NDHWC bf16/fp16 3x3x3 conv / strided conv / transposed conv on tcgen05 tensor cores with fused affine +
+  residual + ReLU.  x (B,D,H,W,Ci) -> (B,Do,Ho,Wo,cout) in the same 16-bit dtype; with out_f32 (cout <= 16, the
+  32->1 classifier) the output and the residual are fp32."""
+  fmt = _fmt(x.dtype)
+  x = _chk(x, x.dtype, 'conv3d_bf16')
+  w_packed = _chk(w_packed, x.dtype, 'conv3d_bf16')
   if x.dim() != 5:
     raise ValueError('conv3d_bf16: expected (B,D,H,W,C) input')
   B, D, H, W, Ci = x.shape
   Do, Ho, Wo = conv3d_out_dims(D, H, W, mode)
-  out = torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+  out = torch.empty((B, Do, Ho, Wo, cout), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
   if residual is not None and residual.shape != out.shape:
     raise RuntimeError('conv3d_bf16: residual shape mismatch')
-  res_bf16 = _opt(residual, torch.bfloat16, 'residual') if not out_f32 else None
+  res_bf16 = _opt(residual, x.dtype, 'residual') if not out_f32 else None
   res_f32 = _opt(residual, torch.float32, 'residual') if out_f32 else None
-  _lib.call('mode_conv3d_bf16', _p(x), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')), _p(res_bf16),
-            _p(res_f32), _p(None if out_f32 else out), _p(out if out_f32 else None), B, Ci, cout, D, H, W, mode, int(relu), _stream())
+  _lib.call('mode_conv3d_tc', _p(x), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')), _p(res_bf16),
+            _p(res_f32), _p(None if out_f32 else out), _p(out if out_f32 else None), B, Ci, cout, D, H, W, mode, int(relu), fmt, _stream())
   return out
 
 
 @conv3d_bf16.register_fake
 def _(x, w_packed, cout, scale, shift, residual, mode, relu, out_f32):
   B, D, H, W, Ci = x.shape
-  return torch.empty((B, *conv3d_out_dims(D, H, W, mode), cout), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+  return torch.empty((B, *conv3d_out_dims(D, H, W, mode), cout), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -262,29 +277,29 @@ def _(x, w_packed, cout, scale, shift, residual, mode, relu, out_f32):
 # ------------------------------------------------------------------------------------------------
 
 
-def nchw_f32_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
-  """(B,C,*spatial) fp32 -> (B,*spatial,C) bf16."""
+def nchw_f32_to_nhwc_bf16(x: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+  """(B,C,*spatial) fp32 -> (B,*spatial,C) bf16 (or fp16 with dtype=torch.float16)."""
   x = _chk(x, torch.float32, 'nchw_f32_to_nhwc_bf16')
   B, Cc = x.shape[:2]
   sp = tuple(x.shape[2:])
   hw = 1
   for s in sp:
     hw *= s
-  y = torch.empty((B, *sp, Cc), dtype=torch.bfloat16, device=x.device)
-  _lib.call('mode_nchw_f32_to_nhwc_bf16', _p(x), _p(y), B, Cc, hw, _stream())
+  y = torch.empty((B, *sp, Cc), dtype=dtype, device=x.device)
+  _lib.call('mode_nchw_f32_to_nhwc_16', _p(x), _p(y), B, Cc, hw, _fmt(dtype), _stream())
   return y
 
 
 def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
-  """(B,*spatial,C) bf16 -> (B,C,*spatial) fp32."""
-  x = _chk(x, torch.bfloat16, 'nhwc_bf16_to_nchw_f32')
+  """(B,*spatial,C) bf16/fp16 -> (B,C,*spatial) fp32."""
+  x = _chk(x, x.dtype, 'nhwc_bf16_to_nchw_f32')
   B, Cc = x.shape[0], x.shape[-1]
   sp = tuple(x.shape[1:-1])
   hw = 1
   for s in sp:
     hw *= s
   y = torch.empty((B, Cc, *sp), dtype=torch.float32, device=x.device)
-  _lib.call('mode_nhwc_bf16_to_nchw_f32', _p(x), _p(y), B, Cc, hw, _stream())
+  _lib.call('mode_nhwc_16_to_nchw_f32', _p(x), _p(y), B, Cc, hw, _fmt(x.dtype), _stream())
   return y
 
 

@@ -144,9 +144,10 @@ def test_conv3d_f32(ops, mode, ci, co, dims):
 # ---------------------------------------------------------------------------- layout helpers
 def test_layout_round_trip(ops):
   x = torch.randn(2, 37, 5, 9, device='cuda')
-  y = ops.nchw_f32_to_nhwc_bf16(x)
-  assert y.shape == (2, 5, 9, 37) and torch.equal(y, x.permute(0, 2, 3, 1).bfloat16())
-  assert torch.equal(ops.nhwc_bf16_to_nchw_f32(y), x.bfloat16().float())
+  for dt in (torch.bfloat16, torch.float16):
+    y = ops.nchw_f32_to_nhwc_bf16(x, dt)
+    assert y.shape == (2, 5, 9, 37) and y.dtype == dt and torch.equal(y, x.permute(0, 2, 3, 1).to(dt))
+    assert torch.equal(ops.nhwc_bf16_to_nchw_f32(y), x.to(dt).float())
 
 
 # ---------------------------------------------------------------------------- a8-a11 geometry
@@ -208,29 +209,30 @@ def test_disp_to_depth_round_trip_full_size(ops):
 
 
 # ---------------------------------------------------------------------------- a5 conv3d on tensor cores (bf16)
-def _tc_case(ops, mode, ci, co, dims, B, seed, relu=True, with_res=True, with_affine=True):
+def _tc_case(ops, mode, ci, co, dims, B, seed, relu=True, with_res=True, with_affine=True, dtype=torch.bfloat16):
   g = torch.Generator().manual_seed(seed)
-  x = torch.randn(B, ci, *dims, generator=g).bfloat16()
+  x = torch.randn(B, ci, *dims, generator=g).to(dtype)
   w = (torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), generator=g) / math.sqrt(27 * ci))
-  wq = w.bfloat16().float()  # the kernel multiplies bf16-rounded weights
+  wq = w.to(dtype).float()  # the kernel multiplies 16-bit-rounded weights
   scale = (torch.rand(co, generator=g) + 0.5) if with_affine else None
   shift = torch.randn(co, generator=g) if with_affine else None
   want = F.conv_transpose3d(x.float(), wq, None, 2, 1, 1) if mode == 2 else F.conv3d(x.float(), wq, None, mode + 1, 1)
-  res = torch.randn(want.shape, generator=g).bfloat16() if with_res else None
+  res = torch.randn(want.shape, generator=g).to(dtype) if with_res else None
   if with_affine:
     want = want * scale.view(1, -1, 1, 1, 1) + shift.view(1, -1, 1, 1, 1)
   if with_res:
     want = want + res.float()
   if relu:
     want = F.relu(want)
-  wp = ops.conv3d_pack_weights(w.cuda(), mode)
+  wp = ops.conv3d_pack_weights(w.cuda(), mode, dtype)
   got = ops.conv3d_bf16(x.permute(0, 2, 3, 4, 1).contiguous().cuda(), wp, co, scale.cuda() if with_affine else None, shift.cuda() if with_affine else None,
                         res.permute(0, 2, 3, 4, 1).contiguous().cuda() if with_res else None, mode, relu, False)
   torch.cuda.synchronize()
   got = got.float().cpu().permute(0, 4, 1, 2, 3)
   assert got.shape == want.shape
   err = (got - want).abs()
-  tol = 2.0**-7 * want.abs().clamp_min(1.0)  # bf16 output rounding (2^-9 rel) + fp32 accumulation-order noise
+  # output rounding (bf16: 2^-9 rel, fp16: 2^-12) + fp32 accumulation-order noise
+  tol = (2.0**-7 if dtype == torch.bfloat16 else 2.0**-10) * want.abs().clamp_min(1.0)
   assert (err <= tol).all(), (mode, ci, co, dims, err.max().item(), (err / tol).max().item())
 
 
@@ -239,6 +241,11 @@ def _tc_case(ops, mode, ci, co, dims, B, seed, relu=True, with_res=True, with_af
 def test_conv3d_bf16_tensor_core(ops, mode, ci, co):
   _tc_case(ops, mode, ci, co, (6, 16, 8), 1, seed=mode * 100 + ci + co)          # exactly one tile column
   _tc_case(ops, mode, ci, co, (5, 22, 13), 2, seed=mode * 100 + ci + co + 1)     # ragged tiles, odd dims, batch 2
+
+
+@pytest.mark.parametrize('mode,ci,co', [(0, 32, 32), (0, 64, 32), (1, 32, 64), (2, 64, 32), (2, 64, 64)])
+def test_conv3d_fp16_tensor_core(ops, mode, ci, co):
+  _tc_case(ops, mode, ci, co, (5, 22, 13), 2, seed=300 + mode + ci + co, dtype=torch.float16)
 
 
 def test_conv3d_bf16_plain_and_large(ops):
@@ -263,20 +270,22 @@ def test_conv3d_bf16_classifier_fp32_out(ops):
 # ---------------------------------------------------------------------------- a2 sphere conv on tensor cores (bf16)
 @pytest.mark.parametrize('B,C,Co,h,w,st', [(1, 64, 128, 16, 8, 'Cassini'), (2, 128, 128, 32, 16, 'Cassini'), (1, 128, 128, 16, 32, 'ERP'), (3, 64, 64, 8, 16, 'ERP'),
                                             (1, 128, 128, 40, 20, 'Cassini')])
-def test_sphere_conv_bf16_tensor_core(ops, B, C, Co, h, w, st):
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_sphere_conv_bf16_tensor_core(ops, B, C, Co, h, w, st, dtype):
   x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 21)
-  xq, wq = x.bfloat16(), wgt.bfloat16()
+  xq, wq = x.to(dtype), wgt.to(dtype)
   scale, shift = torch.rand(Co) + 0.5, torch.randn(Co)
-  res = torch.randn(B, Co, h, w).bfloat16()
+  res = torch.randn(B, Co, h, w).to(dtype)
   want = F.relu(O.sphere_conv(xq.float(), pos, wq.float()) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float())
-  wp = ops.sphere_conv_pack_weights(wgt.cuda())
+  wp = ops.sphere_conv_pack_weights(wgt.cuda(), dtype)
   got = ops.sphere_conv_bf16(xq.permute(0, 2, 3, 1).contiguous().cuda(), pos.cuda(), wp, Co, scale.cuda(), shift.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), True)
   torch.cuda.synchronize()
   got = got.float().cpu().permute(0, 3, 1, 2)
   err = (got - want).abs()
-  # the blended sample is rounded to bf16 before the MMA (the A operand is bf16) and the output is bf16: 2^-7 relative
-  tol = 2.0**-6 * want.abs().clamp_min(1.0)
+  # the blended sample is rounded to 16 bits before the MMA (A operand) and the output is 16-bit
+  rel = 2.0**-6 if dtype == torch.bfloat16 else 2.0**-9
+  tol = rel * want.abs().clamp_min(1.0)
   assert (err <= tol).all(), (err.max().item(), (err / tol).max().item())
   plain = ops.sphere_conv_bf16(xq.permute(0, 2, 3, 1).contiguous().cuda(), pos.cuda(), wp, Co, None, None, None, False).float().cpu().permute(0, 3, 1, 2)
   want_plain = O.sphere_conv(xq.float(), pos, wq.float())
-  assert ((plain - want_plain).abs() <= 2.0**-6 * want_plain.abs().clamp_min(1.0)).all()
+  assert ((plain - want_plain).abs() <= rel * want_plain.abs().clamp_min(1.0)).all()
