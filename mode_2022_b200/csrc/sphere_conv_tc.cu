@@ -15,21 +15,42 @@
 // warps run the epilogue (BN affine + residual + ReLU, bf16 NHWC store).
 //
 // The kernel is gather-bound, not MMA-bound: per 128-pixel tile the corner loads alone are 128 x 9 x 4 x 256 B =
-// 1.18 MB of L1 traffic (~9.2k wavefront cycles) against 4.6k MMA cycles; two CTAs per SM keep both units busy.
+// 1.18 MB of L1 traffic (~9.2k wavefront cycles) against 4.6k MMA cycles.  One CTA (16 gather warps) per SM with a
+// minimal shared-memory carve-out, so that the tile's ~45 KB input neighbourhood stays L1 resident across the 36 re-reads.
 #include "common.cuh"
 using namespace mode;
 
 namespace {
 
-constexpr int kGatherWarps = 8;
-constexpr int kThreadsS = (kGatherWarps + 1) * 32;  // 288
+constexpr int kGatherWarps = 16;
+constexpr int kThreadsS = (kGatherWarps + 1) * 32;  // 544
 constexpr int kStagesS = 3;
 constexpr int kChunkStrideA = 128 * 16 + 16;             // 2064 B: +16 B pad -> conflict-free STS.128 from 8 chunk-lanes
 constexpr int kABytes = ((8 * kChunkStrideA) + 127) & ~127;  // 16640
 
+// packed 16-bit blend: r = w1*v1 + w2*v2 + w3*v3 + w4*v4 on two channels at once (HFMA2.BF16 / HFMA2): 4 instructions per
+// channel pair instead of 2 unpacks + 8 FFMAs + a pack.  The gather is instruction-issue bound (ncu: IPC 2.0, tensor pipe
+// 8 % active), so this is the lever; the price is that the partial sums are rounded to the storage format.
+template <int FMT>
+__device__ __forceinline__ uint32_t blend2(uint32_t w1, uint32_t v1, uint32_t w2, uint32_t v2, uint32_t w3, uint32_t v3, uint32_t w4, uint32_t v4) {
+  if (FMT == kFmtBF16) {
+    const __nv_bfloat162 r = __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w4), *reinterpret_cast<__nv_bfloat162*>(&v4),
+                             __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w3), *reinterpret_cast<__nv_bfloat162*>(&v3),
+                             __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w2), *reinterpret_cast<__nv_bfloat162*>(&v2),
+                             __hmul2(*reinterpret_cast<__nv_bfloat162*>(&w1), *reinterpret_cast<__nv_bfloat162*>(&v1)))));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __half2 r = __hfma2(*reinterpret_cast<__half2*>(&w4), *reinterpret_cast<__half2*>(&v4),
+                      __hfma2(*reinterpret_cast<__half2*>(&w3), *reinterpret_cast<__half2*>(&v3),
+                      __hfma2(*reinterpret_cast<__half2*>(&w2), *reinterpret_cast<__half2*>(&v2),
+                      __hmul2(*reinterpret_cast<__half2*>(&w1), *reinterpret_cast<__half2*>(&v1)))));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+
 struct ScParams {
   const uint16_t* x;    // (B,H,W,C) bf16
-  const float* pos;     // (18,H,W) fp32
+  const int4* table;    // [9][H*W] x {int4 corner pixel index (-1 = dropped), float4 bilinear weight}: built once per grid
   const uint16_t* wpk;  // [9][C/64][8][Co][8] bf16
   const float* scale;
   const float* shift;
@@ -90,7 +111,7 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) &
 __host__ __device__ constexpr uint32_t make_idesc(int n, int fmt) { return (1u << 4) | ((fmt == 0 ? 1u : 0u) << 7) | ((fmt == 0 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
 
 template <int FMT>
-__global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScParams p) {
+__global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -127,34 +148,28 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
 
   if (warp < kGatherWarps) {
     // =================================================== gather producers (+ epilogue)
-    const int tid = threadIdx.x;  // 0..255
+    const int tid = threadIdx.x;  // 0..511
     const int kc = tid & 7;       // 8-channel chunk inside the 64-channel half
     uint32_t stage = 0, tile_n = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tile_n) {
       for (int k = 0; k < 9; ++k) {
-        // per-(pixel, tap) sampling parameters for this thread's 4 pixels
-        float w1[4], w2[4], w3[4], w4[4];
-        long long o1[4], o2[4], o3[4], o4[4];  // element offsets of the four corners (-1 = dropped)
+        // per-(pixel, tap) sampling parameters for this thread's 4 pixels, from the precomputed gather table
+        // (the grid is a constant of the layer: floor / weights / edge rules are evaluated once per resolution)
+        uint32_t w1[2], w2[2], w3[2], w4[2];  // bilinear weights, duplicated into both 16-bit halves
+        uint32_t o1[2], o2[2], o3[2], o4[2];  // element offsets of the four corners
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const long long gp = (long long)tile * 128 + (tid >> 3) + 32 * j;
-          o1[j] = o2[j] = o3[j] = o4[j] = -1;
-          w1[j] = w2[j] = w3[j] = w4[j] = 0.f;
+        for (int j = 0; j < 2; ++j) {
+          const long long gp = (long long)tile * 128 + (tid >> 3) + 64 * j;
+          o1[j] = o2[j] = o3[j] = o4[j] = 0;
+          w1[j] = w2[j] = w3[j] = w4[j] = 0;
           if (gp < p.npix) {
             const int b = (int)(gp / HW), pp = (int)(gp - (long long)b * HW);
-            const float h_im = __ldg(p.pos + (size_t)(2 * k) * HW + pp);
-            const float w_im = __ldg(p.pos + (size_t)(2 * k + 1) * HW + pp);
-            if (h_im > -1 && w_im > -1 && h_im < p.H && w_im < p.W) {  // kernel.cu:246
-              const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-              const int h_high = h_low + 1, w_high = w_low + 1;
-              const float lh = h_im - h_low, lw = w_im - w_low, hh = 1 - lh, hw = 1 - lw;
-              w1[j] = hh * hw, w2[j] = hh * lw, w3[j] = lh * hw, w4[j] = lh * lw;  // kernel.cu:109
-              const long long base = (long long)b * HW;
-              if (h_low >= 0 && w_low >= 0) o1[j] = (base + (long long)h_low * p.W + w_low) * p.C;
-              if (h_low >= 0 && w_high <= p.W - 1) o2[j] = (base + (long long)h_low * p.W + w_high) * p.C;
-              if (h_high <= p.H - 1 && w_low >= 0) o3[j] = (base + (long long)h_high * p.W + w_low) * p.C;
-              if (h_high <= p.H - 1 && w_high <= p.W - 1) o4[j] = (base + (long long)h_high * p.W + w_high) * p.C;
-            }
+            const int4 ix = __ldg(p.table + 2 * ((size_t)k * HW + pp));
+            const float4 wt = __ldg(reinterpret_cast<const float4*>(p.table + 2 * ((size_t)k * HW + pp) + 1));
+            const uint32_t base = (uint32_t)b * (uint32_t)HW;
+            w1[j] = pack2<FMT>(wt.x, wt.x), w2[j] = pack2<FMT>(wt.y, wt.y), w3[j] = pack2<FMT>(wt.z, wt.z), w4[j] = pack2<FMT>(wt.w, wt.w);
+            o1[j] = (base + (uint32_t)ix.x) * (uint32_t)p.C, o2[j] = (base + (uint32_t)ix.y) * (uint32_t)p.C;
+            o3[j] = (base + (uint32_t)ix.z) * (uint32_t)p.C, o4[j] = (base + (uint32_t)ix.w) * (uint32_t)p.C;
           }
         }
         for (int half = 0; half < nhalf; ++half, ++stage) {
@@ -168,27 +183,24 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
             for (uint32_t i = tid; i < b_bytes / 16; i += kGatherWarps * 32) cp_async16(b_s + i * 16, wsrc + i * 8);
             asm volatile("cp.async.commit_group;" ::: "memory");
           }
-          const int coff = half * 64 + kc * 8;
+          const uint32_t coff = (uint32_t)(half * 64 + kc * 8);
+          uint4 v1[2], v2[2], v3[2], v4[2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            const uint4 v1 = o1[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o1[j] + coff)) : z;
-            const uint4 v2 = o2[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o2[j] + coff)) : z;
-            const uint4 v3 = o3[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o3[j] + coff)) : z;
-            const uint4 v4 = o4[j] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.x + o4[j] + coff)) : z;
-            const uint32_t a1[4] = {v1.x, v1.y, v1.z, v1.w}, a2[4] = {v2.x, v2.y, v2.z, v2.w}, a3[4] = {v3.x, v3.y, v3.z, v3.w},
-                           a4[4] = {v4.x, v4.y, v4.z, v4.w};
-            uint32_t o[4];
+          for (int j = 0; j < 2; ++j) {  // all 8 corner loads in flight before the first use
+            v1[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)(o1[j] + coff)));
+            v2[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)(o2[j] + coff)));
+            v3[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)(o3[j] + coff)));
+            v4[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)(o4[j] + coff)));
+          }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float l1, h1, l2, h2, l3, h3, l4, h4;
-              unpack2<FMT>(a1[q], l1, h1), unpack2<FMT>(a2[q], l2, h2), unpack2<FMT>(a3[q], l3, h3), unpack2<FMT>(a4[q], l4, h4);
-              const float lo = (w1[j] * l1 + w2[j] * l2 + w3[j] * l3 + w4[j] * l4);
-              const float hi = (w1[j] * h1 + w2[j] * h2 + w3[j] * h3 + w4[j] * h4);
-              o[q] = pack2<FMT>(lo, hi);
-            }
-            const int pix_l = (tid >> 3) + 32 * j;
-            *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int j = 0; j < 2; ++j) {
+            uint4 o;
+            o.x = blend2<FMT>(w1[j], v1[j].x, w2[j], v2[j].x, w3[j], v3[j].x, w4[j], v4[j].x);
+            o.y = blend2<FMT>(w1[j], v1[j].y, w2[j], v2[j].y, w3[j], v3[j].y, w4[j], v4[j].y);
+            o.z = blend2<FMT>(w1[j], v1[j].z, w2[j], v2[j].z, w3[j], v3[j].z, w4[j], v4[j].z);
+            o.w = blend2<FMT>(w1[j], v1[j].w, w2[j], v2[j].w, w3[j], v3[j].w, w4[j], v4[j].w);
+            const int pix_l = (tid >> 3) + 64 * j;
+            *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = o;
           }
           asm volatile("cp.async.wait_group 0;" ::: "memory");
           fence_proxy_async();
@@ -196,12 +208,13 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
           if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
         }
       }
-      // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns [64*(w/4), +64)
+      // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column group w/4 of ngrp (4 groups when Co % 128 == 0, else 2)
       mbar_wait(smem_u32(tfull_bar), tile_n & 1);
       tc_fence_after();
-      const int q = warp & 3, hcol = warp >> 2;
+      const int ngrp = (p.Co % 128 == 0) ? 4 : 2;
+      const int q = warp & 3, grp = warp >> 2;
       const long long gp = (long long)tile * 128 + q * 32 + lane;
-      for (int c0 = hcol * (p.Co / 2); c0 < (hcol + 1) * (p.Co / 2); c0 += 32) {
+      for (int c0 = grp * (p.Co / ngrp); grp < ngrp && c0 < (grp + 1) * (p.Co / ngrp); c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -273,6 +286,37 @@ __global__ void __launch_bounds__(kThreadsS, 2) sphere_conv_tc_kernel(const ScPa
   if (warp == kGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
+// gather table: for every (tap, pixel) the four corner pixel indices and bilinear weights, with the reference's rules
+// (kernel.cu:246 tap guard, :97-107 per-corner guards, :109 weights).  Depends only on the sampling grid.
+__global__ void sphere_table_kernel(const float* __restrict__ pos, int4* __restrict__ table, int H, int W, int KK) {
+  const int HW = H * W;
+  const long long n = (long long)KK * HW;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e / HW), pp = (int)(e - (long long)k * HW);
+    const float h_im = pos[(size_t)(2 * k) * HW + pp], w_im = pos[(size_t)(2 * k + 1) * HW + pp];
+    int4 ix = make_int4(-1, -1, -1, -1);
+    float4 wt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
+      const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+      const int h_high = h_low + 1, w_high = w_low + 1;
+      const float lh = h_im - h_low, lw = w_im - w_low, hh = 1 - lh, hw = 1 - lw;
+      wt = make_float4(hh * hw, hh * lw, lh * hw, lh * lw);
+      if (h_low >= 0 && w_low >= 0) ix.x = h_low * W + w_low;
+      if (h_low >= 0 && w_high <= W - 1) ix.y = h_low * W + w_high;
+      if (h_high <= H - 1 && w_low >= 0) ix.z = h_high * W + w_low;
+      if (h_high <= H - 1 && w_high <= W - 1) ix.w = h_high * W + w_high;
+    }
+    // dropped corners: weight 0 and a valid dummy index, so the gather needs no predication (0 * x == 0 for finite x;
+    // the reference never reads those pixels -- the only observable difference would be an Inf/NaN at pixel 0)
+    if (ix.x < 0) ix.x = 0, wt.x = 0.f;
+    if (ix.y < 0) ix.y = 0, wt.y = 0.f;
+    if (ix.z < 0) ix.z = 0, wt.z = 0.f;
+    if (ix.w < 0) ix.w = 0, wt.w = 0.f;
+    table[2 * e] = ix;
+    table[2 * e + 1] = *reinterpret_cast<int4*>(&wt);
+  }
+}
+
 // (Co, C, 3, 3) fp32 -> [tap 9][half C/64][chunk 8][n Co][8] bf16
 __global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __restrict__ wp, int C, int Co, int fmt, long long total) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -301,27 +345,42 @@ extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_h16* w_packed,
   return MODE_OK;
 }
 
-extern "C" int mode_sphere_conv_tc(const mode_h16* x, const float* pos, const mode_h16* w_packed, const float* scale, const float* shift,
+extern "C" size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw) { return (size_t)32 * Kh * Kw * H * W; }
+
+extern "C" int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, void* stream) {
+  MODE_CHECK_ARG(pos && table && H > 0 && W > 0 && Kh > 0 && Kw > 0, "sphere_conv_build_table: bad arguments");
+  const long long n = (long long)Kh * Kw * H * W;
+  sphere_table_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, (int4*)table, H, W, Kh * Kw);
+  MODE_CHECK_LAUNCH("sphere_conv_build_table");
+  return MODE_OK;
+}
+
+extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const mode_h16* w_packed, const float* scale, const float* shift,
                                    const mode_h16* residual, mode_h16* out, int B, int C, int H, int W, int Co, int relu, int fmt, void* stream) {
   MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "sphere_conv_tc: fmt must be 0 (bf16) or 1 (fp16)");
-  MODE_CHECK_ARG(x && pos && w_packed && out, "sphere_conv_tc: null pointer");
+  MODE_CHECK_ARG(x && table && w_packed && out, "sphere_conv_tc: null pointer");
   MODE_CHECK_ARG(B > 0 && H > 0 && W > 0, "sphere_conv_tc: bad shape");
   MODE_CHECK_ARG(C > 0 && C % 64 == 0, "sphere_conv_tc: C (%d) must be a multiple of 64 (use the f32 kernel otherwise)", C);
   MODE_CHECK_ARG(Co >= 64 && Co <= 256 && Co % 64 == 0, "sphere_conv_tc: Co (%d) must be 64, 128, 192 or 256", Co);
   ScParams p;
-  p.x = x, p.pos = pos, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.out = out;
+  p.x = x, p.table = (const int4*)table, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.out = out;
   p.B = B, p.C = C, p.H = H, p.W = W, p.Co = Co, p.relu = relu;
   p.npix = (long long)B * H * W;
-  MODE_CHECK_ARG((p.npix + 127) / 128 < 2147483647LL, "sphere_conv_tc: too many tiles");
+  MODE_CHECK_ARG(p.npix * C < 4294967295LL, "sphere_conv_tc: activation tensor too large for 32-bit offsets");
   p.ntiles = (int)((p.npix + 127) / 128);
   const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + (2 * kStagesS + 2) * 8 + 16;
   static thread_local size_t attr = 0;
   if (smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
     MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
+    // one CTA per SM: leave the rest of the 228 KB to L1 -- the 9 taps x 4 corners of a tile re-read the same ~45 KB
+    // of input, which must stay L1 resident (with a maximal carve-out the kernel was L2-bandwidth bound: 3.6 GB/launch)
+    const int carve = (int)((smem + 8 * 1024) * 100 / (228 * 1024)) + 1;
+    cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtBF16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtFP16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     attr = smem;
   }
-  const int grid = std::min(p.ntiles, 2 * kNumSMs);
+  const int grid = std::min(p.ntiles, kNumSMs);
   if (fmt == kFmtBF16)
     sphere_conv_tc_kernel<kFmtBF16><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
   else

@@ -24,15 +24,44 @@ class _FoldedConv2d:
     self.b = shift.to(dtype)
     self.stride, self.padding, self.dilation = conv.stride, conv.padding, conv.dilation
 
-  def __call__(self, x, relu):
+  def __call__(self, x, relu, residual=None):
+    """conv + folded-BN bias [+ residual] [+ ReLU]; uses cuDNN's fused conv-bias-(add)-ReLU when available."""
+    if _FUSED_CUDNN and relu:
+      if residual is None:
+        return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding, self.dilation, 1)
+      return torch.cudnn_convolution_add_relu(x, self.w, residual, 1.0, self.b, self.stride, self.padding, self.dilation, 1)
     y = F.conv2d(x, self.w, self.b, self.stride, self.padding, self.dilation)
+    if residual is not None:
+      y = y.add_(residual)
     return F.relu_(y) if relu else y
+
+
+def _probe_fused_cudnn():
+  """cuDNN runtime-fused conv+bias(+add)+ReLU for channels_last 16-bit tensors (plain cuDNN calls)."""
+  try:
+    for dt in (torch.bfloat16, torch.float16):
+      x = torch.randn(1, 32, 8, 8, device='cuda', dtype=dt).contiguous(memory_format=torch.channels_last)
+      w = torch.randn(32, 32, 3, 3, device='cuda', dtype=dt).contiguous(memory_format=torch.channels_last)
+      b = torch.randn(32, device='cuda', dtype=dt)
+      ref = F.relu(F.conv2d(x, w, b, 1, 1) + x)
+      got = torch.cudnn_convolution_add_relu(x, w, x, 1.0, b, (1, 1), (1, 1), (1, 1), 1)
+      got2 = torch.cudnn_convolution_relu(x, w, b, (1, 1), (1, 1), (1, 1), 1)
+      if not (torch.allclose(got.float(), ref.float(), atol=0.25, rtol=0.05) and torch.allclose(got2.float(), F.relu(F.conv2d(x, w, b, 1, 1)).float(), atol=0.25, rtol=0.05)):
+        return False
+    return True
+  except Exception:
+    return False
+
+
+_FUSED_CUDNN = False
 
 
 class Bf16Plan(_PlanBase):
   def __init__(self, model, dtype=torch.bfloat16):
+    global _FUSED_CUDNN
     self.dtype = dtype
     self.sphere_impl = 'bf16'
+    _FUSED_CUDNN = _probe_fused_cudnn()
     super().__init__(model)
     fe = model.feature_extraction
     if model.conv_type != 'Sphere':
@@ -65,9 +94,8 @@ class Bf16Plan(_PlanBase):
   # ---- 2-D feature extractor: bf16 channels_last (physically NHWC) ------------------------------
   def _regular_layer(self, x, blocks):
     for c1, c2, ds in blocks:
-      out = c2(c1(x, True), False)
       res = ds(x, False) if ds is not None else x
-      x = F.relu_(out.add_(res))
+      x = c2(c1(x, True), True, residual=res)  # relu(conv2(relu(conv1(x))) + res), reference submodule.py:108-119
     return x
 
   def features(self, x):
