@@ -21,17 +21,20 @@
 //     contiguous again; transposed convs keep 4 accumulators per output plane (one per output parity class).
 //   * all 27 x Cin x NT weights stay resident in shared memory for the CTA's lifetime.
 //
-// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quadrant = warp id), warp 4 = MMA issuer (one thread),
-// warps 5-8 = producers (cp.async with zero-fill for the padding, then fence.proxy.async + mbarrier arrive).
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quadrant = warp id), warp 4 = MMA issuer (one elected lane),
+// warp 5 = TMA producer: one cp.async.bulk.tensor (4-D box {8 ch, w, h, 1 plane}) per 8-channel chunk lands each halo
+// plane directly in the UMMA layout; out-of-bounds box elements are zero-filled by the TMA unit = the conv padding.
 // Pipelines: smem ring full/empty (producer <-> MMA), TMEM set full/empty (MMA <-> epilogue).
+#include <cuda.h>
+
 #include "common.cuh"
 using namespace mode;
 
 namespace {
 
-constexpr int kEpiWarps = 4, kProdWarps = 4;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 288
-constexpr int kMaxSlots = 6;
+constexpr int kEpiWarps = 4, kProdWarps = 1;
+constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 192
+constexpr int kMaxSlots = 8;
 constexpr int kMaxSets = 32;  // TMEM accumulator blocks (512 columns / NT) or sets (transposed conv)
 constexpr int kStageCh = 32;  // channels per pipeline stage (one "K half" when Cin = 64)
 
@@ -56,15 +59,15 @@ template <int MODE>
 struct Geo;
 template <>
 struct Geo<0> {  // stride 1: halo 18 x 10
-  static constexpr int HV = 18, WV = 10, NV = 180, ROW = 10, NLOAD = 180, ACCS = 1;
+  static constexpr int HV = 18, WV = 10, ROW = 10, ACCS = 1, NBOX = 4, BOX_BYTES = 18 * 10 * 16, BOX_STRIDE = 2944;
 };
 template <>
-struct Geo<1> {  // stride 2: halo 33 x 17 stored as 4 parity sub-planes of 17 x 9
-  static constexpr int HV = 33, WV = 17, NV = 4 * 153, ROW = 9, NLOAD = 33 * 17, ACCS = 1;
+struct Geo<1> {  // stride 2: halo 33 x 17 loaded as 4 parity sub-planes of 17 x 9 (TMA traversal stride 2), layout [parity][chunk]
+  static constexpr int HV = 33, WV = 17, ROW = 9, ACCS = 1, NBOX = 16, BOX_BYTES = 17 * 9 * 16, BOX_STRIDE = 2560;
 };
 template <>
 struct Geo<2> {  // transposed stride 2: halo 17 x 9 (one extra row/col on the high side), 4 parity accumulators
-  static constexpr int HV = 17, WV = 9, NV = 153, ROW = 9, NLOAD = 153, ACCS = 4;
+  static constexpr int HV = 17, WV = 9, ROW = 9, ACCS = 4, NBOX = 4, BOX_BYTES = 17 * 9 * 16, BOX_STRIDE = 2560;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -248,7 +251,7 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
 __host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
 
 template <int MODE, int NT, int FMT>
-__global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
@@ -256,8 +259,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
   if (p.dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   const int lane = threadIdx.x & 31;
   const int KH = p.Cin / kStageCh;                       // K halves (1 or 2)
-  constexpr uint32_t kSlotBytes = G::NV * kStageCh * 2;  // one stage: NV voxels x 32 ch bf16
-  constexpr uint32_t kChunkStride = G::NV * 16;          // bytes between 8-channel chunks of a stage
+  constexpr uint32_t kSlotBytes = G::NBOX * G::BOX_STRIDE;  // one stage: 32 channels of one halo plane
+  constexpr uint32_t kChunkStride = G::BOX_STRIDE;          // bytes between 8-channel chunks of a stage (128 B aligned)
   const uint32_t w_bytes = (uint32_t)KH * 27 * 4 * NT * 16;
   // TMEM: mode 0/1 use a ring of R = 512/NT accumulator blocks (one per output plane in flight); mode 2 a ring of 3
   // sets x 4 parity classes.
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nslots; ++i) {
-      mbar_init(smem_u32(full_bar + i), kProdWarps);
+      mbar_init(smem_u32(full_bar + i), 1);
       mbar_init(smem_u32(empty_bar + i), 1);
     }
     for (int i = 0; i < R; ++i) {
@@ -317,59 +320,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
   tc_fence_after();
 
   if (warp >= kEpiWarps + 1) {
-    // =========================================================== PRODUCERS
-    const int ptid = threadIdx.x - (kEpiWarps + 1) * 32;  // 0..127
-    uint32_t stage = 0;  // global stage counter (ring position + phase)
-    // Up to `la` stages of cp.async groups are kept in flight per thread (la = min(4, nslots - 1)); a stage is
-    // published (fence.proxy.async + mbarrier arrive) when its group has landed.
-    const int la = min(4, p.nslots - 1);
-    uint32_t issued = 0, published = 0;
-    auto publish_one = [&](int allow_in_flight) {
-      switch (allow_in_flight) {
-        case 0: cp_async_wait<0>(); break;
-        case 1: cp_async_wait<1>(); break;
-        case 2: cp_async_wait<2>(); break;
-        case 3: cp_async_wait<3>(); break;
-        default: cp_async_wait<4>(); break;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(full_bar + (published % p.nslots)));
-      ++published;
-    };
-    for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
-      const Item it = decode_item(p, nb_of_cta * per_nb + li);
-      int p0, p1, o0, o1;
-      chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
-      const int h0 = it.th * 16, w0 = it.tw * 8;
-      const int gh0 = (MODE == 0) ? h0 - 1 : (MODE == 1) ? 2 * h0 - 1 : h0;
-      const int gw0 = (MODE == 0) ? w0 - 1 : (MODE == 1) ? 2 * w0 - 1 : w0;
-      for (int pl = p0; pl <= p1; ++pl) {
-        for (int kh = 0; kh < KH; ++kh, ++stage) {
-          const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
-          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
-          const uint32_t sbase = smem_u32(slots_s + (size_t)slot * kSlotBytes);
-          const uint16_t* xp = p.x + ((size_t)(it.b * p.Di + pl) * p.Hi) * p.Wi * p.Cin + kh * kStageCh;
-          for (int i = ptid; i < G::NLOAD * 4; i += kProdWarps * 32) {
-            const int kc = i & 3, v = i >> 2;
-            const int hv = v / G::WV, wv = v - hv * G::WV;
-            const int gh = gh0 + hv, gw = gw0 + wv;
-            const bool ok = gh >= 0 && gh < p.Hi && gw >= 0 && gw < p.Wi;
-            int sv;
-            if (MODE == 1)
-              sv = (((hv & 1) << 1) | (wv & 1)) * 153 + (hv >> 1) * 9 + (wv >> 1);
-            else
-              sv = v;
-            const uint16_t* src = ok ? xp + ((size_t)gh * p.Wi + gw) * p.Cin + kc * 8 : p.x;
-            cp_async16(sbase + kc * kChunkStride + sv * 16, src, ok ? 16u : 0u);
+    // =========================================================== TMA PRODUCER (one lane)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+      uint32_t slot = 0, phase = 0;
+      for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
+        const Item it = decode_item(p, nb_of_cta * per_nb + li);
+        int p0, p1, o0, o1;
+        chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+        const int h0 = it.th * 16, w0 = it.tw * 8;
+        const int gh0 = (MODE == 0) ? h0 - 1 : (MODE == 1) ? 2 * h0 - 1 : h0;
+        const int gw0 = (MODE == 0) ? w0 - 1 : (MODE == 1) ? 2 * w0 - 1 : w0;
+        for (int pl = p0; pl <= p1; ++pl) {
+          const int plane = it.b * p.Di + pl;
+          for (int kh = 0; kh < KH; ++kh) {
+            mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+            const uint32_t bar = smem_u32(full_bar + slot);
+            const uint32_t sbase = smem_u32(slots_s + (size_t)slot * kSlotBytes);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::NBOX * G::BOX_BYTES)) : "memory");
+#pragma unroll
+            for (int bx = 0; bx < G::NBOX; ++bx) {
+              const int kc = bx & 3, q = bx >> 2;  // q: parity sub-plane (stride-2 only)
+              const int cw = gw0 + (q & 1), chh = gh0 + (q >> 1);
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                      sbase + (uint32_t)bx * G::BOX_STRIDE),
+                  "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(kh * kStageCh + kc * 8), "r"(cw), "r"(chh), "r"(plane), "r"(bar)
+                  : "memory");
+            }
+            if (++slot == (uint32_t)p.nslots) slot = 0, phase ^= 1;
           }
-          cp_async_commit();
-          ++issued;
-          if ((int)(issued - published) > la) publish_one(la);
         }
       }
     }
-    while (published < issued) publish_one((int)(issued - published) - 1);
   } else if (warp == kEpiWarps) {
     // =========================================================== MMA ISSUER
     // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; a single
@@ -433,11 +416,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
                 const int th_ = t / 3, tw_ = t % 3;
-                const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_)
-                                                  : (uint32_t)((((th_ & 1) << 1) | (tw_ & 1)) * 153 + (th_ >> 1) * 9 + (tw_ >> 1));
+                // byte offset of the tap's view inside the stage (stride 2: parity sub-plane q, then (kh>>1, kw>>1))
+                const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_) * 16
+                                                  : (uint32_t)(((th_ & 1) << 1) | (tw_ & 1)) * (4 * kChunkStride) + (uint32_t)((th_ >> 1) * 9 + (tw_ >> 1)) * 16;
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks)
-                  umma_bf16_lh(d1, a_lo + ((ks * 2 * kChunkStride + voff * 16) >> 4), a_hi, b0 + (((uint32_t)(t * 4 + ks * 2) * (3 * NT * 16)) >> 4), b_hi,
+                  umma_bf16_lh(d1, a_lo + ((ks * 2 * kChunkStride + voff) >> 4), a_hi, b0 + (((uint32_t)(t * 4 + ks * 2) * (3 * NT * 16)) >> 4), b_hi,
                                i1, 1u);
               }
               if (kh == KH - 1) {
@@ -678,20 +662,53 @@ __global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restric
 
 int pick_nt(int Co) { return Co >= 32 ? 32 : 16; }
 
+// 4-D tensor map over the NDHWC activation: dims (C, W, H, B*D), box {8 ch, WV, HV, 1}; stride-2 layers traverse w/h with
+// element stride 2 (one box per parity).  Out-of-bounds elements (halo outside the volume) are zero-filled by the TMA unit.
+int make_tmap(CUtensorMap* tm, const void* x, int fmt, int C, int Wi, int Hi, long long planes, int mode) {
+  static decltype(&cuTensorMapEncodeTiled) encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      set_error("conv3d_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return MODE_ECUDA;
+    }
+    encode = reinterpret_cast<decltype(&cuTensorMapEncodeTiled)>(fn);
+  }
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)planes};
+  const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wi * C * 2, (cuuint64_t)Hi * Wi * C * 2};
+  cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+  if (mode == 0) {
+    box[0] = 8, box[1] = 10, box[2] = 18, box[3] = 1;
+  } else if (mode == 1) {
+    box[0] = 8, box[1] = 18, box[2] = 34, box[3] = 1;  // ceil(18/2) = 9 columns, ceil(34/2) = 17 rows
+    estr[1] = 2, estr[2] = 2;
+  } else {
+    box[0] = 8, box[1] = 9, box[2] = 17, box[3] = 1;
+  }
+  const CUresult r = encode(tm, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv3d_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return MODE_ECUDA;
+  }
+  return MODE_OK;
+}
+
 template <int MODE, int NT, int FMT>
-int launch_tc2(const TcParams& p, int grid, size_t smem, cudaStream_t s) {
+int launch_tc2(const TcParams& p, const CUtensorMap& tm, int grid, size_t smem, cudaStream_t s) {
   static thread_local size_t attr = 0;
   if (smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
     attr = smem;
   }
-  conv3d_tc_kernel<MODE, NT, FMT><<<grid, kThreads, smem, s>>>(p);
+  conv3d_tc_kernel<MODE, NT, FMT><<<grid, kThreads, smem, s>>>(p, tm);
   MODE_CHECK_LAUNCH("conv3d_tc");
   return MODE_OK;
 }
 template <int MODE, int NT>
-int launch_tc(const TcParams& p, int fmt, int grid, size_t smem, cudaStream_t s) {
-  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, grid, smem, s);
+int launch_tc(const TcParams& p, const CUtensorMap& tm, int fmt, int grid, size_t smem, cudaStream_t s) {
+  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, tm, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, tm, grid, smem, s);
 }
 
 }  // namespace
@@ -750,7 +767,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   // shared memory: resident weights + stage ring
   const int KH = Ci / kStageCh;
   const size_t w_bytes = ((size_t)KH * 27 * 4 * NT * 16 + 127) & ~(size_t)127;
-  const size_t slot_bytes = (size_t)(mode == 0 ? Geo<0>::NV : mode == 1 ? Geo<1>::NV : Geo<2>::NV) * kStageCh * 2;
+  const size_t slot_bytes = (size_t)(mode == 0 ? Geo<0>::NBOX * Geo<0>::BOX_STRIDE : mode == 1 ? Geo<1>::NBOX * Geo<1>::BOX_STRIDE : Geo<2>::NBOX * Geo<2>::BOX_STRIDE);
   const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128;
   const size_t budget = 227 * 1024;
   int nslots = (int)std::min<size_t>(kMaxSlots, (budget - w_bytes - misc) / slot_bytes);
@@ -783,13 +800,18 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   const int grid = ctas_per_nb * p.nblk;
   const size_t smem = w_bytes + (size_t)nslots * slot_bytes + misc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (NT == 32) {
-    if (mode == 0) return launch_tc<0, 32>(p, fmt, grid, smem, s);
-    if (mode == 1) return launch_tc<1, 32>(p, fmt, grid, smem, s);
-    return launch_tc<2, 32>(p, fmt, grid, smem, s);
+  CUtensorMap tm;
+  {
+    const int rc = make_tmap(&tm, x, fmt, Ci, Wi, Hi, (long long)B * Di, mode);
+    if (rc != MODE_OK) return rc;
   }
-  if (mode == 0) return launch_tc<0, 16>(p, fmt, grid, smem, s);
-  if (mode == 1) return launch_tc<1, 16>(p, fmt, grid, smem, s);
+  if (NT == 32) {
+    if (mode == 0) return launch_tc<0, 32>(p, tm, fmt, grid, smem, s);
+    if (mode == 1) return launch_tc<1, 32>(p, tm, fmt, grid, smem, s);
+    return launch_tc<2, 32>(p, tm, fmt, grid, smem, s);
+  }
+  if (mode == 0) return launch_tc<0, 16>(p, tm, fmt, grid, smem, s);
+  if (mode == 1) return launch_tc<1, 16>(p, tm, fmt, grid, smem, s);
   set_error("conv3d_tc: unsupported configuration");
   return MODE_ENOSUP;
 }

@@ -5,9 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mode_2022_b200 import ops, _lib
 lib = _lib.load()
 dev = 'cuda'
-ci, co, dims, mode = 32, 32, (48, 256, 128), 0
+ci, co, dims, mode = [int(v) for v in os.environ.get('CFG', '32,32,48,256,128,0').split(',')][:2] + [tuple(int(v) for v in os.environ.get('CFG', '32,32,48,256,128,0').split(',')[2:5])] + [int(os.environ.get('CFG', '32,32,48,256,128,0').split(',')[5])]
 x = torch.randn(1, *dims, ci, device=dev).bfloat16()
-w = torch.randn(co, ci, 3, 3, 3, device=dev) / math.sqrt(27 * ci)
+w = torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), device=dev) / math.sqrt(27 * ci)
 wp = ops.conv3d_pack_weights(w, mode)
 for _ in range(3):
   ops.conv3d_bf16(x, wp, co, None, None, None, mode, True, False)
