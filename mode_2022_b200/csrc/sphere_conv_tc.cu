@@ -23,7 +23,7 @@ using namespace mode;
 namespace {
 
 constexpr int kGatherWarps = 16;
-constexpr int kThreadsS = (kGatherWarps + 1) * 32;  // 544
+constexpr int kThreadsS = (kGatherWarps + 2) * 32;  // 576: 16 gather/epilogue warps, MMA warp, weight-loader warp
 constexpr int kStagesS = 3;
 constexpr int kChunkStrideA = 128 * 16 + 16;             // 2064 B: +16 B pad -> conflict-free STS.128 from 8 chunk-lanes
 constexpr int kABytes = ((8 * kChunkStrideA) + 127) & ~127;  // 16640
@@ -59,6 +59,7 @@ struct ScParams {
   int B, C, H, W, Co, relu;
   long long npix;       // B*H*W
   int ntiles;
+  int tw, th, tiles_x, tiles_y;  // tile = th x tw pixels (th*tw == 128); tw == 0: linear tiles of 128 consecutive pixels
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,9 +107,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+// global pixel index (b*HW + y*W + x) of row r of tile t, or -1 beyond the tensor.  2-D tiles (th x tw) keep the tile's
+// input neighbourhood compact (10 x 18 pixels instead of 3 full image rows), which is what makes the 36 corner re-reads hit L1.
+struct ScParams;
+__device__ __forceinline__ long long tile_pixel(const ScParams& p, int tile, int r, int HW);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3FFF) | (1u << 14); }
 __host__ __device__ constexpr uint32_t make_idesc(int n, int fmt) { return (1u << 4) | ((fmt == 0 ? 1u : 0u) << 7) | ((fmt == 0 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | (8u << 24); }
+
+__device__ __forceinline__ long long tile_pixel(const ScParams& p, int tile, int r, int HW) {
+  if (p.tw == 0) {
+    const long long gp = (long long)tile * 128 + r;
+    return gp < p.npix ? gp : -1;
+  }
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int b = tile / per_img, t = tile - b * per_img;
+  const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+  const int y = ty * p.th + r / p.tw, x = tx * p.tw + r % p.tw;
+  return (long long)b * HW + (long long)y * p.W + x;
+}
 
 template <int FMT>
 __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScParams p) {
@@ -127,7 +144,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStagesS; ++i) {
-      mbar_init(smem_u32(full_bar + i), kGatherWarps);
+      mbar_init(smem_u32(full_bar + i), kGatherWarps + 1);  // 16 gather warps + the weight loader's expect_tx arrive
       mbar_init(smem_u32(empty_bar + i), 1);
     }
     mbar_init(smem_u32(tfull_bar), 1);
@@ -161,8 +178,8 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
       bool inb[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const long long gp = (long long)tile * 128 + (tid >> 3) + 64 * j;
-        inb[j] = gp < p.npix;
+        const long long gp = tile_pixel(p, tile, (tid >> 3) + 64 * j, HW);
+        inb[j] = gp >= 0;
         const int b = inb[j] ? (int)(gp / HW) : 0;
         pp[j] = inb[j] ? (int)(gp - (long long)b * HW) : 0;
         base[j] = (uint32_t)b * (uint32_t)HW;
@@ -204,13 +221,6 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
           const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
           mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
           uint8_t* a_s = smem + (size_t)slot * stage_bytes;
-          const uint32_t b_s = smem_u32(a_s + kABytes);
-          // weight slab (tap k, half): contiguous b_bytes in the packed layout
-          {
-            const uint16_t* wsrc = p.wpk + ((size_t)(k * nhalf + half) * b_bytes) / 2;
-            for (uint32_t i = tid; i < b_bytes / 16; i += kGatherWarps * 32) cp_async16(b_s + i * 16, wsrc + i * 8);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-          }
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             uint4 o;
@@ -221,7 +231,6 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
             const int pix_l = (tid >> 3) + 64 * j;
             *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = o;
           }
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
@@ -232,12 +241,12 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
       tc_fence_after();
       const int ngrp = (p.Co % 128 == 0) ? 4 : 2;
       const int q = warp & 3, grp = warp >> 2;
-      const long long gp = (long long)tile * 128 + q * 32 + lane;
+      const long long gp = tile_pixel(p, tile, q * 32 + lane, HW);
       for (int c0 = grp * (p.Co / ngrp); grp < ngrp && c0 < (grp + 1) * (p.Co / ngrp); c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (gp < p.npix) {
+        if (gp >= 0) {
           const uint16_t* rp = p.res ? p.res + gp * p.Co + c0 : nullptr;
           uint16_t* op = p.out + gp * p.Co + c0;
 #pragma unroll
@@ -274,6 +283,24 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty_bar));
+    }
+  } else if (warp == kGatherWarps + 1) {
+    // =================================================== weight loader: one bulk copy (TMA, 1-D) per stage, up to kStagesS ahead
+    if (lane == 0) {
+      uint32_t stage = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        for (int s2 = 0; s2 < nstage_tile; ++s2, ++stage) {
+          const int half = s2 / 9, k = s2 - half * 9;
+          const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
+          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+          const uint32_t bar = smem_u32(full_bar + slot);
+          const uint32_t dst = smem_u32(smem + (size_t)slot * stage_bytes + kABytes);
+          const uint16_t* wsrc = p.wpk + ((size_t)(k * nhalf + half) * b_bytes) / 2;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(wsrc), "r"(b_bytes), "r"(bar)
+                       : "memory");
+        }
+      }
     }
   } else {
     // =================================================== MMA issuer (warp-uniform control flow, one elected lane issues)
@@ -386,7 +413,13 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
   p.B = B, p.C = C, p.H = H, p.W = W, p.Co = Co, p.relu = relu;
   p.npix = (long long)B * H * W;
   MODE_CHECK_ARG(p.npix * C < 4294967295LL, "sphere_conv_tc: activation tensor too large for 32-bit offsets");
-  p.ntiles = (int)((p.npix + 127) / 128);
+  if (W % 16 == 0 && H % 8 == 0) {
+    p.tw = 16, p.th = 8, p.tiles_x = W / 16, p.tiles_y = H / 8;
+    p.ntiles = B * p.tiles_x * p.tiles_y;
+  } else {
+    p.tw = 0, p.th = 0, p.tiles_x = p.tiles_y = 0;
+    p.ntiles = (int)((p.npix + 127) / 128);
+  }
   const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + (2 * kStagesS + 2) * 8 + 16;
   static thread_local size_t attr = 0;
   if (smem > attr) {

@@ -118,3 +118,33 @@ def test_h16_end_to_end_vs_reference_golden(name, precision):
   print(f'{name}: {precision} end-to-end EPE vs fp32 reference = {epe:.4f} px (max {np.abs(pred - z["pred"]).max():.3f}); conf mean abs diff {np.abs(conf - z["conf"]).mean():.4f}')
   assert np.isfinite(pred).all() and pred.min() >= 0 and pred.max() <= D - 1 + 1e-3
   assert epe <= E2E_EPE[precision], epe
+
+
+def test_two_stage_pipeline_in_memory():
+  """BASELINE config[3] shape at test size: 6-pair stereo stage -> in-memory stage boundary (disp->depth, rotate / z-buffer
+  warp into camera 1's frame, no npz/PNG round trip) -> ModeFusion.  The boundary is checked against the oracle's disp2depth
+  on the same disparity/confidence maps; the fusion net only for shape/range (plain cuDNN, interface parity)."""
+  from mode_2022_b200.models import ModeFusion
+  from mode_2022_b200.utils.geometry import StageBoundary, CAM_PAIRS
+  sd, (H, W, D, st, seed), z = Hh.golden_state_dict('small_cassini')
+  m = _model('small_cassini', 'fp16', sd, H, W, D, st)
+  g = torch.Generator().manual_seed(7)
+  left, right = torch.randn(6, 3, H, W, generator=g).cuda(), torch.randn(6, 3, H, W, generator=g).cuda()
+  disp, conf = m(left, right)
+  assert disp.shape == conf.shape == (6, 1, H, W)
+  depths, confs = StageBoundary()(disp, conf)
+  assert len(depths) == len(confs) == 6 and all(d.shape == (1, 1, H, W) for d in depths)
+  dn, cn = disp.cpu().numpy(), conf.cpu().numpy()
+  for i, pair in enumerate(CAM_PAIRS):
+    od, oc = O.disp2depth(dn[i, 0], cn[i, 0], pair)
+    gd, gc = depths[i][0, 0].cpu().numpy(), confs[i][0, 0].cpu().numpy()
+    bad = (np.abs(gd - od.astype(np.float32)) > 1e-3 * np.maximum(1.0, np.abs(od))) | (np.abs(gc - oc) > 1e-5)
+    assert bad.mean() <= 5e-3, (pair, bad.mean())
+  fusion = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}).cuda().eval()
+  rgbs = [torch.randn(1, 3, H, W, device='cuda') for _ in range(4)]
+  with torch.no_grad():
+    out = fusion([d.float() for d in depths], [c.float() for c in confs], rgbs)
+  assert out.shape == (1, 1, H, W) and torch.isfinite(out).all() and out.min() >= 0 and out.max() <= 20.0
+  # the uint8 confidence quantisation of the file pipeline (save_output_disparity_stage.py:199) can be emulated
+  dq, cq = StageBoundary(quantise_conf=True)(disp, conf)
+  assert all(torch.equal(torch.round(c * 255), c * 255) or (torch.round(c * 255) - c * 255).abs().max() < 1e-3 for c in cq)
