@@ -52,6 +52,7 @@ struct TcParams {
   int tiles_h, tiles_w, nchunks, chunk, nblk;  // chunk: output planes per item (mode 0/1), input planes (mode 2)
   int total_items;
   int nslots, relu;
+  int tmem_cols;             // 512 (one CTA per SM) or 256 (two co-resident CTAs: two independent MMA issue streams)
   long long* dbg;            // optional per-CTA timing records [grid][4]: smid, t_start, t_end, n_items (profiling aid)
 };
 
@@ -251,7 +252,7 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
 __host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
 
 template <int MODE, int NT, int FMT>
-__global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
@@ -265,9 +266,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
   // TMEM: mode 0/1 use a ring of R = 512/NT accumulator blocks (one per output plane in flight); mode 2 a ring of 3
   // sets x 4 parity classes.
   constexpr int kSetCols = G::ACCS * NT;
-  constexpr int R = (MODE == 2) ? 3 : 512 / NT;
-  constexpr int kTmemCols = 512;
-  static_assert(R * kSetCols <= 512 && R <= kMaxSets, "TMEM ring overflow");
+  const int R = (MODE == 2) ? 3 : p.tmem_cols / NT;
+  const uint32_t kTmemCols = (uint32_t)p.tmem_cols;
+  static_assert(3 * 4 * NT <= 512 && 512 / NT <= kMaxSets, "TMEM ring overflow");
 
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps) {  // the MMA warp owns the TMEM allocation
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // Work distribution: items are nb-major (nb = output-channel block); the grid is split into nblk equal groups of
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
   const uint32_t tmem_base = *tmem_ptr_s;
   if (MODE != 2 && warp < kEpiWarps) {
     // depth-stacked MMAs always accumulate: every accumulator block starts at zero (and is re-zeroed by the epilogue)
-    for (int c = 0; c < 512; c += 32) tmem_zero<32>(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    for (int c = 0; c < p.tmem_cols; c += 32) tmem_zero<32>(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -365,78 +366,138 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
     // use_mask holds the mbarrier phase parity of every block (toggled per use).  mode 2: set = job % R.
     uint32_t stage = 0, job_base = 0, use_mask = 0;
     uint32_t slot = 0, phase = 0;
-    long long dbg_tempty = 0, dbg_full = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    long long dbg_tempty = 0, dbg_full = 0, dbg_grp = 0, dbg_t0 = p.dbg ? clock64() : 0;
     int dbg_nst = 0;
     const uint32_t a_lo0 = desc_lo(smem_u32(slots_s), kChunkStride);
     const uint32_t b_lo0 = desc_lo(w_base, (MODE == 2 ? 1 : 3) * NT * 16);
     uint32_t a_lo = a_lo0;
+    if (MODE != 2) {
+      // ---- depth-stacked issue, software pipelined.  One stage = (input plane, 32-channel half) = 18 MMAs (9 in-plane taps x
+      // 2 K steps) with N = nb*NT covering the nb <= 3 output planes fed by this input plane (weight blocks [wb, wb+nb)).
+      // The tensor pipe drains one N=96 MMA per ~56 cycles and queues only ~8 of them, while a stage's bookkeeping (window
+      // arithmetic, two mbarrier try_waits of ~90 cycles each, commits, iterator advance) costs the issuing warp ~1000 cycles.
+      // Run back to back (issue 18, then bookkeep) the pipe idled ~45 % of the time.  Here the bookkeeping of stage s+1 is cut
+      // into three slices that execute between the three 6-MMA groups of stage s, i.e. while the queue is still full.
+      int li = lane_cta;
+      bool have = li < per_nb;
+      Item it;
+      int p0 = 0, p1 = -1, o0 = 0, o1 = 0, nout = 0, pl = 0, kh = 0, next_new = 0, next_done = 0;
+      auto begin_item = [&]() {
+        it = decode_item(p, nb_of_cta * per_nb + li);
+        chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+        nout = o1 - o0, pl = p0, kh = 0, next_new = 0, next_done = 0;
+      };
+      auto window = [&](int& oa, int& ob, int& wb) {
+        if (MODE == 0) {
+          const int rel = pl - o0;
+          oa = max(rel - 1, 0), ob = min(rel + 1, nout - 1), wb = oa - rel + 1;
+        } else {
+          const int rel2 = pl - (2 * o0 - 1);
+          if (!(rel2 & 1)) {
+            const int od1 = (rel2 >> 1) - 1;
+            oa = max(od1, 0), ob = min(od1 + 1, nout - 1), wb = oa - od1;
+          } else {
+            oa = ob = rel2 >> 1, wb = 2;
+          }
+        }
+      };
+      auto wait_new_blocks = [&](int ob) {  // first touch of a block: the epilogue must have drained + zeroed it
+        const long long c0 = p.dbg ? clock64() : 0;
+        for (; next_new <= ob; ++next_new) {
+          mbar_wait(smem_u32(tempty_bar + next_new), ((use_mask >> next_new) & 1) ^ 1);
+          use_mask ^= 1u << next_new;
+        }
+        if (p.dbg) dbg_tempty += clock64() - c0;
+      };
+      auto wait_full = [&](uint32_t sl, uint32_t ph) {
+        const long long c0 = p.dbg ? clock64() : 0;
+        mbar_wait(smem_u32(full_bar + sl), ph);
+        if (p.dbg) {
+          dbg_full += clock64() - c0;
+          if (blockIdx.x < 4 && dbg_nst < 60 && lane == 0) p.dbg[8 * gridDim.x + blockIdx.x * 64 + dbg_nst] = clock64() - dbg_t0;
+          ++dbg_nst;
+        }
+        tc_fence_after();
+      };
+      auto issue_taps = [&](int t0, uint32_t d1, uint32_t i1, uint32_t a_cur, uint32_t b0) {
+#pragma unroll
+        for (int t = t0; t < t0 + 3; ++t) {
+          const int th_ = t / 3, tw_ = t % 3;
+          // byte offset of the tap's view inside the stage (stride 2: parity sub-plane q, then (kh>>1, kw>>1))
+          const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_) * 16
+                                            : (uint32_t)(((th_ & 1) << 1) | (tw_ & 1)) * (4 * kChunkStride) + (uint32_t)((th_ >> 1) * 9 + (tw_ >> 1)) * 16;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_bf16_lh(d1, a_cur + ((ks * 2 * kChunkStride + voff) >> 4), a_hi, b0 + (((uint32_t)(t * 4 + ks * 2) * (3 * NT * 16)) >> 4), b_hi, i1, 1u);
+        }
+      };
+      // ---- prologue: first stage prepared with blocking waits
+      int c_oa = 0, c_ob = -1, c_wb = 0;
+      if (have) {
+        begin_item();
+        window(c_oa, c_ob, c_wb);
+        wait_new_blocks(c_ob);
+        wait_full(slot, phase);
+      }
+      while (have) {
+        // parameters of the CURRENT stage
+        const uint32_t i1 = make_idesc((c_ob - c_oa + 1) * NT, FMT);
+        const uint32_t d1 = tmem_base + (uint32_t)c_oa * NT;
+        const uint32_t b0 = b_lo0 + (uint32_t)kh * ((27 * 4 * NT * 16) >> 4) + (uint32_t)c_wb * ((NT * 16) >> 4);
+        const uint32_t a_cur = a_lo, cur_slot = slot;
+        const int cur_pl = pl, cur_p1 = p1, cur_o0 = o0, cur_ob = c_ob, cur_nd0 = next_done;
+        const bool cur_last_kh = (kh == KH - 1);
+        long long g0 = p.dbg ? clock64() : 0;
+        if (elect_one()) issue_taps(0, d1, i1, a_cur, b0);
+        __syncwarp();
+        if (p.dbg) dbg_grp += clock64() - g0;
+        // ---- slice A (queue full): completed-block count of the current stage, iterator advance, next window
+        int ncommit = 0;
+        if (cur_last_kh) {
+          // block b is complete after its last contributing plane: o0+b+1 (mode 0) / 2(o0+b)+1 (mode 1), or the item's last plane
+          while (next_done <= cur_ob && (cur_pl == cur_p1 || cur_pl == ((MODE == 0) ? cur_o0 + next_done + 1 : 2 * (cur_o0 + next_done) + 1))) ++next_done, ++ncommit;
+        }
+        bool new_plane = false, new_item = false;
+        if (++kh == KH) {
+          kh = 0, new_plane = true;
+          if (++pl > p1) {
+            li += ctas_per_nb;
+            have = li < per_nb;
+            new_item = true;
+            if (have) begin_item();
+          }
+        }
+        if (++slot == (uint32_t)p.nslots) slot = 0, phase ^= 1, a_lo = a_lo0;
+        else a_lo += kSlotBytes >> 4;
+        int n_oa = c_oa, n_ob = c_ob, n_wb = c_wb;
+        if (have && new_plane) window(n_oa, n_ob, n_wb);
+        g0 = p.dbg ? clock64() : 0;
+        if (elect_one()) issue_taps(3, d1, i1, a_cur, b0);
+        __syncwarp();
+        if (p.dbg) dbg_grp += clock64() - g0;
+        // ---- slice B: TMEM blocks first touched by the next stage.  (Across an item boundary the block may be one whose
+        // completion is only committed below -- short chunks -- so that wait moves behind the commits.)
+        if (have && new_plane && !new_item) wait_new_blocks(n_ob);
+        g0 = p.dbg ? clock64() : 0;
+        if (elect_one()) {
+          issue_taps(6, d1, i1, a_cur, b0);
+          for (int nd = cur_nd0; nd < cur_nd0 + ncommit; ++nd) umma_commit(smem_u32(tfull_bar + nd));  // accumulator complete -> epilogue
+          umma_commit(smem_u32(empty_bar + cur_slot));                                                 // stage consumed -> TMA may refill it
+        }
+        __syncwarp();
+        if (p.dbg) dbg_grp += clock64() - g0;
+        // ---- slice C: operands of the next stage
+        if (have && new_item) wait_new_blocks(n_ob);
+        if (have) wait_full(slot, phase);
+        c_oa = n_oa, c_ob = n_ob, c_wb = n_wb;
+      }
+    } else {
     for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
       const Item it = decode_item(p, nb_of_cta * per_nb + li);
       int p0, p1, o0, o1;
       chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
-      const int nout = o1 - o0;
-      int next_new = 0, next_done = 0;
       for (int pl = p0; pl <= p1; ++pl) {
-        if (MODE != 2) {
-          // ---- depth-stacked issue: output blocks [oa, ob] (relative to o0) fed by this input plane, weight blocks
-          //      [wb_a, wb_a + nb).  The issuing warp is latency-bound on its own instruction stream (a 56-cycle MMA
-          //      leaves ~12 instructions of budget), so the bookkeeping below is kept to a few integer ops per plane.
-          int oa, ob, wb_a;
-          if (MODE == 0) {
-            const int rel = pl - o0;
-            oa = max(rel - 1, 0), ob = min(rel + 1, nout - 1), wb_a = oa - rel + 1;
-          } else {
-            const int rel2 = pl - (2 * o0 - 1);
-            if (!(rel2 & 1)) {
-              const int od1 = (rel2 >> 1) - 1;
-              oa = max(od1, 0), ob = min(od1 + 1, nout - 1), wb_a = oa - od1;
-            } else {
-              oa = ob = rel2 >> 1, wb_a = 2;
-            }
-          }
-          const uint32_t i1 = make_idesc((ob - oa + 1) * NT, FMT);
-          const uint32_t d1 = tmem_base + (uint32_t)oa * NT;
-          long long c0 = p.dbg ? clock64() : 0;
-          for (; next_new <= ob; ++next_new) {  // first touch of a block: the epilogue must have drained + zeroed it
-            mbar_wait(smem_u32(tempty_bar + next_new), ((use_mask >> next_new) & 1) ^ 1);
-            use_mask ^= 1u << next_new;
-          }
-          if (p.dbg) dbg_tempty += clock64() - c0;
-          for (int kh = 0; kh < KH; ++kh) {
-            c0 = p.dbg ? clock64() : 0;
-            mbar_wait(smem_u32(full_bar + slot), phase);
-            if (p.dbg) {
-              dbg_full += clock64() - c0;
-              if (blockIdx.x < 4 && dbg_nst < 60 && lane == 0) p.dbg[8 * gridDim.x + blockIdx.x * 64 + dbg_nst] = clock64() - dbg_t0;
-              ++dbg_nst;
-            }
-            tc_fence_after();
-            if (elect_one()) {
-              const uint32_t b0 = b_lo0 + (uint32_t)kh * ((27 * 4 * NT * 16) >> 4) + (uint32_t)wb_a * ((NT * 16) >> 4);
-#pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                const int th_ = t / 3, tw_ = t % 3;
-                // byte offset of the tap's view inside the stage (stride 2: parity sub-plane q, then (kh>>1, kw>>1))
-                const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_) * 16
-                                                  : (uint32_t)(((th_ & 1) << 1) | (tw_ & 1)) * (4 * kChunkStride) + (uint32_t)((th_ >> 1) * 9 + (tw_ >> 1)) * 16;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                  umma_bf16_lh(d1, a_lo + ((ks * 2 * kChunkStride + voff) >> 4), a_hi, b0 + (((uint32_t)(t * 4 + ks * 2) * (3 * NT * 16)) >> 4), b_hi,
-                               i1, 1u);
-              }
-              if (kh == KH - 1) {
-                // block b is complete after its last contributing plane: o0+b+1 (mode 0) / 2(o0+b)+1 (mode 1), or the item's last plane
-                for (int nd = next_done; nd <= ob && (pl == p1 || pl == ((MODE == 0) ? o0 + nd + 1 : 2 * (o0 + nd) + 1)); ++nd)
-                  umma_commit(smem_u32(tfull_bar + nd));
-              }
-              umma_commit(smem_u32(empty_bar + slot));  // stage consumed -> producers may refill it
-            }
-            __syncwarp();
-            if (++slot == (uint32_t)p.nslots) slot = 0, phase ^= 1, a_lo = a_lo0;
-            else a_lo += kSlotBytes >> 4;
-          }
-          while (next_done <= ob && (pl == p1 || pl == ((MODE == 0) ? o0 + next_done + 1 : 2 * (o0 + next_done) + 1))) ++next_done;
-        } else {
+        {
           // ---- transposed conv: per output plane a set of 4 parity-class accumulators
           for (int kh = 0; kh < KH; ++kh, ++stage) {
             const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
@@ -491,9 +552,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
       }
       job_base += (uint32_t)(o1 - o0);
     }
+    }
     if (p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 8 + 4] = dbg_tempty;
       p.dbg[blockIdx.x * 8 + 5] = dbg_full;
+      p.dbg[blockIdx.x * 8 + 3] = dbg_grp;
       p.dbg[blockIdx.x * 8 + 6] = clock64() - dbg_t0;
     }
   } else {
@@ -614,10 +677,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const TcParams p
     p.dbg[blockIdx.x * 8 + 0] = smid;
     p.dbg[blockIdx.x * 8 + 1] = t_start;
     p.dbg[blockIdx.x * 8 + 2] = t1;
-    p.dbg[blockIdx.x * 8 + 3] = (per_nb - lane_cta + ctas_per_nb - 1) / ctas_per_nb;
+    // slot 3: cycles the MMA warp spent inside its issue groups (written by the MMA warp)
   }
   if (warp == kEpiWarps) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -770,14 +833,26 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   const size_t slot_bytes = (size_t)(mode == 0 ? Geo<0>::NBOX * Geo<0>::BOX_STRIDE : mode == 1 ? Geo<1>::NBOX * Geo<1>::BOX_STRIDE : Geo<2>::NBOX * Geo<2>::BOX_STRIDE);
   const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128;
   const size_t budget = 227 * 1024;
-  int nslots = (int)std::min<size_t>(kMaxSlots, (budget - w_bytes - misc) / slot_bytes);
+  // Two co-resident CTAs per SM when they fit (stride-1 / stride-2 layers with <= 55 KB of weights): the MMA-issuing warp is
+  // bound by its own instruction latency (~1700 cycles of waits + bookkeeping + issue per 18-MMA stage against ~1000 cycles of
+  // tensor-pipe work, measured with the per-CTA timers), so two independent issue streams keep the pipe fed.  Each CTA then
+  // owns 256 TMEM columns (8 accumulator blocks of 32) instead of 512.
+  int ctas_per_sm = 1;
+  if (mode != 2) {
+    const size_t half = (budget - 2048) / 2;
+    if (w_bytes + misc + 3 * slot_bytes <= half) ctas_per_sm = 2;
+  }
+  const size_t cta_budget = ctas_per_sm == 2 ? (budget - 2048) / 2 : budget;
+  int nslots = (int)std::min<size_t>(kMaxSlots, (cta_budget - w_bytes - misc) / slot_bytes);
   MODE_CHECK_ARG(nslots >= 2, "conv3d_tc: not enough shared memory for a 2-stage pipeline");
   p.nslots = nslots;
+  p.tmem_cols = ctas_per_sm == 2 ? 256 : 512;
+  const int sm_slots = kNumSMs * ctas_per_sm;
   // depth chunking: split the depth range into nch BALANCED chunks (chunk = ceil(d / nch)); pick the nch that minimises
   // the critical-path stage count  rounds x (chunk + halo)  (persistent CTAs, round-robin items).
   const long long cols = (long long)B * p.tiles_h * p.tiles_w;
   const int halo = (mode == 0) ? 2 : 1;
-  const int max_chunk = (mode == 2) ? d_dim : 512 / NT;  // mode 0/1: one TMEM accumulator block per output plane of the chunk
+  const int max_chunk = (mode == 2) ? d_dim : p.tmem_cols / NT;  // mode 0/1: one TMEM accumulator block per output plane of the chunk
   int best_chunk = std::min(d_dim, max_chunk);
   double best = 1e30;
   for (int nch = 1; nch <= d_dim; ++nch) {
@@ -785,7 +860,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
     if (c > max_chunk) continue;
     const int nch_eff = ceil_div(d_dim, c);
     const long long items = cols * nch_eff;
-    const long long ctas = std::min<long long>(items, kNumSMs / p.nblk);
+    const long long ctas = std::min<long long>(items, sm_slots / p.nblk);
     const long long rounds = (items + ctas - 1) / ctas;
     const double stages = (double)(mode == 1 ? 2 * c + halo : c + halo);
     const double cost = (double)rounds * (stages + 1.5);  // +1.5: per-item pipeline ramp
@@ -796,7 +871,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   const long long per_nb = cols * p.nchunks;
   MODE_CHECK_ARG(per_nb * p.nblk < 2147483647LL, "conv3d_tc: too many work items");
   p.total_items = (int)(per_nb * p.nblk);
-  const int ctas_per_nb = (int)std::min<long long>(per_nb, kNumSMs / p.nblk);
+  const int ctas_per_nb = (int)std::min<long long>(per_nb, sm_slots / p.nblk);
   const int grid = ctas_per_nb * p.nblk;
   const size_t smem = w_bytes + (size_t)nslots * slot_bytes + misc;
   cudaStream_t s = (cudaStream_t)stream;

@@ -39,9 +39,9 @@ bysm = sorted(zip(sm, dur.tolist()))
 print('dur by smid:')
 print(' '.join('%d:%d' % (a, round(b)) for a, b in bysm))
 
-print('MMA warp cycles: cta, total, wait_tempty, wait_full | epilogue warp0 wait_tfull')
+print('MMA warp cycles: cta, total, wait_tempty, wait_full, in_mma_groups | epilogue warp0 wait_tfull')
 for i in (0, 1, 2, 3, 4, 5, 6, 7, 144, 145, 146, 147):
-  print(i, d[i, 6].item(), d[i, 4].item(), d[i, 5].item(), '|', d[i, 7].item())
+  print(i, d[i, 6].item(), d[i, 4].item(), d[i, 5].item(), d[i, 3].item(), '|', d[i, 7].item())
 
 for c in range(4):
   ts = st[c, :60].tolist()

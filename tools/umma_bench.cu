@@ -34,13 +34,25 @@ struct Cfg {
   int epi;      // 1: warps 1-3 hammer TMEM with tcgen05.ld/st on columns 448.. while the MMAs run
 };
 
-__global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
+__global__ void __launch_bounds__(160, 1) bench_kernel(Cfg c, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar, dummy_bar;
   __shared__ volatile int done_flag;
   __shared__ uint32_t tmem_ptr;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
+    uint32_t v = 0;
+    if (c.rot_d == 7) {  // hash -> two bf16 values with random sign / mantissa, exponent in [2^-3, 2)
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 97u;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+      const uint32_t lo = ((h & 0x8000u) | ((0x7c + ((h >> 7) & 3)) << 7) | (h & 0x7f)) & 0xffffu;
+      const uint32_t hi = (((h >> 16) & 0x8000u) | ((0x7c + ((h >> 23) & 3)) << 7) | ((h >> 16) & 0x7f)) & 0xffffu;
+      v = lo | (hi << 16);
+    } else if (c.rot_d == 8) {
+      v = 0x3f803f80u;  // all ones
+    }
+    reinterpret_cast<uint32_t*>(smem)[i] = v;
+  }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"(smem_u32(&dummy_bar)));
@@ -72,10 +84,9 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
 #pragma unroll
         for (int t = 0; t < 18; ++t) {
           uint32_t dd = d;
-          if (c.rot_d) dd = tmem + (t % 3) * 96;  // compile-time pattern after unrolling
           umma(dd, ad0 + (uint64_t)(t & 7) * (c.a_step >> 4), bd0 + (uint64_t)(t & 7) * (c.b_step >> 4), idesc, 1u);
         }
-        if (c.commit) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy_bar)) : "memory");
+        if (c.commit && c.commit < 1000) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy_bar)) : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     }
@@ -90,7 +101,7 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
     done_flag = 1;
   } else if (c.epi) {
     uint32_t v[32];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 448;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c.b_sbo * 0 + (uint32_t)c.a_step * 0 + (uint32_t)(c.commit >= 1000 ? c.commit - 1000 : 448);
     while (!done_flag) {
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]) : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -112,23 +123,19 @@ int main() {
     const char* name;
     Cfg c;
   } cfgs[] = {
-      // name, {n, layout, a_lbo, a_sbo, b_lbo, b_sbo, a_step, b_step, rot_d, iters, win, commit, epi}
-      {"N=96 same D", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 0, 0, 0}},
-      {"N=96 window shift every 18", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 18, 0, 0}},
-      {"N=96 window shift every 36", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 36, 0, 0}},
-      {"N=96 same D + commit every 18", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 0, 18, 0}},
-      {"N=96 window 18 + commit 18", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 18, 18, 0}},
-      {"N=96 same D + TMEM ld/st hammer", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 0, 0, 1}},
-      {"N=96 same D + TMEM ld/st every ~1us", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 0, 0, 1000}},
-      {"N=96 window 18 + commit + ld/st ~1us", {96, 0, 2880, 160, 1536, 128, 16, 6144, 0, 4608, 18, 18, 1000}},
-      {"N=128 same D", {128, 0, 2880, 160, 2048, 128, 16, 8192, 0, 4608, 0, 0, 0}},
-      {"N=128 window shift every 18", {128, 0, 2880, 160, 2048, 128, 16, 8192, 0, 4608, 18, 0, 0}},
-      {"N=48 same D (classifier)", {48, 0, 2880, 160, 768, 128, 16, 3072, 0, 4608, 0, 0, 0}},
-      {"N=64 window shift every 18", {64, 0, 2880, 160, 1024, 128, 16, 4096, 0, 4608, 18, 0, 0}},
+      // name, {n, layout, a_lbo, a_sbo, b_lbo, b_sbo, a_step, b_step, data(0 zeros, 7 random, 8 ones), iters, win, commit, epi}
+      {"N=96  zeros", {96, 0, 2944, 160, 1536, 128, 16, 6144, 0, 9216, 18, 18, 0}},
+      {"N=96  ones", {96, 0, 2944, 160, 1536, 128, 16, 6144, 8, 9216, 18, 18, 0}},
+      {"N=96  random bf16", {96, 0, 2944, 160, 1536, 128, 16, 6144, 7, 9216, 18, 18, 0}},
+      {"N=256 zeros", {256, 0, 2048, 128, 4096, 128, 4096, 8192, 0, 9216, 0, 0, 0}},
+      {"N=256 random bf16", {256, 0, 2048, 128, 4096, 128, 4096, 8192, 7, 9216, 0, 0, 0}},
+      {"N=32  random bf16", {32, 0, 2944, 160, 1536, 128, 16, 6144, 7, 9216, 18, 18, 0}},
+      {"N=64  random bf16", {64, 0, 2944, 160, 1536, 128, 16, 6144, 7, 9216, 18, 18, 0}},
+      {"N=128 random bf16", {128, 0, 2944, 160, 2048, 128, 16, 8192, 7, 9216, 18, 18, 0}},
   };
   for (auto& nc : cfgs) {
     for (int grid : {148}) {
-      bench_kernel<<<grid, 128, 200 * 1024>>>(nc.c, d_out);
+      bench_kernel<<<grid, 160, 200 * 1024>>>(nc.c, d_out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
         printf("%-45s grid=%3d ERROR %s\n", nc.name, grid, cudaGetErrorString(e));
