@@ -36,7 +36,7 @@ constexpr int kEpiWarps = 4, kProdWarps = 1;
 constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 192
 constexpr int kMaxSlots = 8;
 constexpr int kMaxSets = 32;  // TMEM accumulator blocks (512 columns / NT) or sets (transposed conv)
-constexpr int kStageCh = 32;  // channels per pipeline stage (one "K half" when Cin = 64)
+constexpr int kWHalf = 32;  // the packed weights are organised in 32-input-channel halves
 
 struct TcParams {
   const uint16_t* x;         // (B, Di, Hi, Wi, Cin) bf16
@@ -60,15 +60,15 @@ template <int MODE>
 struct Geo;
 template <>
 struct Geo<0> {  // stride 1: halo 18 x 10
-  static constexpr int HV = 18, WV = 10, ROW = 10, ACCS = 1, NBOX = 4, BOX_BYTES = 18 * 10 * 16, BOX_STRIDE = 2944;
+  static constexpr int HV = 18, WV = 10, ROW = 10, ACCS = 1, NBOX = 1, NVOX = 180;
 };
 template <>
 struct Geo<1> {  // stride 2: halo 33 x 17 loaded as 4 parity sub-planes of 17 x 9 (TMA traversal stride 2), layout [parity][chunk]
-  static constexpr int HV = 33, WV = 17, ROW = 9, ACCS = 1, NBOX = 16, BOX_BYTES = 17 * 9 * 16, BOX_STRIDE = 2560;
+  static constexpr int HV = 33, WV = 17, ROW = 9, ACCS = 1, NBOX = 4, NVOX = 153;
 };
 template <>
 struct Geo<2> {  // transposed stride 2: halo 17 x 9 (one extra row/col on the high side), 4 parity accumulators
-  static constexpr int HV = 17, WV = 9, ROW = 9, ACCS = 4, NBOX = 4, BOX_BYTES = 17 * 9 * 16, BOX_STRIDE = 2560;
+  static constexpr int HV = 17, WV = 9, ROW = 9, ACCS = 4, NBOX = 1, NVOX = 153;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -179,7 +179,9 @@ __device__ __forceinline__ void umma_bf16_lh(uint32_t d_tmem, uint32_t a_lo, uin
       : "memory");
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14); }  // version 1 at bit 46
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout = 0) {  // version 1 at bit 46, layout type at bits 61-63
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29);
+}
 
 // UMMA shared-memory descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B, rows 16 B apart;
 // LBO = byte distance between the two 16-byte K chunks of one MMA, SBO = byte distance between 8-row groups.
@@ -251,18 +253,27 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
 //   mode 1: odd input planes feed kd = 2 (block 0) and kd = 0 (block 1); even planes feed kd = 1 (block 2)
 __host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
 
-template <int MODE, int NT, int FMT>
+template <int MODE, int NT, int FMT, int SC>
 __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE>;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle patterns are anchored at 1024-byte boundaries
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
   long long t_start = 0;
   if (p.dbg != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   const int lane = threadIdx.x & 31;
-  const int KH = p.Cin / kStageCh;                       // K halves (1 or 2)
-  constexpr uint32_t kSlotBytes = G::NBOX * G::BOX_STRIDE;  // one stage: 32 channels of one halo plane
-  constexpr uint32_t kChunkStride = G::BOX_STRIDE;          // bytes between 8-channel chunks of a stage (128 B aligned)
-  const uint32_t w_bytes = (uint32_t)KH * 27 * 4 * NT * 16;
+  // A stage = SC channels (SC*2-byte rows) of one halo plane, laid out [h][w][SC] with the TMA/UMMA hardware swizzle of the row
+  // width (64 B -> SWIZZLE_64B, 128 B -> SWIZZLE_128B): one TMA element per voxel instead of one per 16-byte chunk (with
+  // un-swizzled 16-byte elements the TMA writes alone kept the shared-memory port busy ~720 cycles per 1010-cycle stage).
+  // A tap view is still just a shifted descriptor start address: the swizzle XOR is a function of the absolute shared-memory
+  // address for both the TMA write and the UMMA read, so any row-aligned start inside a 1024-byte-aligned box is consistent.
+  constexpr uint32_t RB = SC * 2;                                        // row bytes
+  constexpr uint32_t kLayoutA = (SC == 32) ? 4u : 2u;                    // UMMA layout type: SWIZZLE_64B / SWIZZLE_128B
+  constexpr uint32_t kBoxStride = (G::NVOX * RB + 1023) & ~1023u;
+  constexpr uint32_t kSlotBytes = G::NBOX * kBoxStride;
+  constexpr int KS = SC / 16;                                            // MMA K steps per tap and stage
+  const int KH = p.Cin / SC;                                             // stages per plane (2 only for stride-2 layers with Cin = 64)
+  const uint32_t w_bytes = (uint32_t)(p.Cin / kWHalf) * 27 * 4 * NT * 16;
   // TMEM: mode 0/1 use a ring of R = 512/NT accumulator blocks (one per output plane in flight); mode 2 a ring of 3
   // sets x 4 parity classes.
   constexpr int kSetCols = G::ACCS * NT;
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
 
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
-  uint8_t* slots_s = smem + ((w_bytes + 127) & ~127u);
+  uint8_t* slots_s = smem + ((w_bytes + 1023) & ~1023u);  // swizzled boxes: 1024-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(slots_s + (size_t)p.nslots * kSlotBytes);
   uint64_t* full_bar = bars;                               // [nslots] producers -> MMA
   uint64_t* empty_bar = bars + kMaxSlots;                  // [nslots] MMA (commit) -> producers
@@ -338,15 +349,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
             mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
             const uint32_t bar = smem_u32(full_bar + slot);
             const uint32_t sbase = smem_u32(slots_s + (size_t)slot * kSlotBytes);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::NBOX * G::BOX_BYTES)) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::NBOX * G::NVOX * RB)) : "memory");
 #pragma unroll
-            for (int bx = 0; bx < G::NBOX; ++bx) {
-              const int kc = bx & 3, q = bx >> 2;  // q: parity sub-plane (stride-2 only)
+            for (int q = 0; q < G::NBOX; ++q) {  // q: parity sub-plane (stride-2 only)
               const int cw = gw0 + (q & 1), chh = gh0 + (q >> 1);
               asm volatile(
                   "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-                      sbase + (uint32_t)bx * G::BOX_STRIDE),
-                  "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(kh * kStageCh + kc * 8), "r"(cw), "r"(chh), "r"(plane), "r"(bar)
+                      sbase + (uint32_t)q * kBoxStride),
+                  "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(kh * SC), "r"(cw), "r"(chh), "r"(plane), "r"(bar)
                   : "memory");
             }
             if (++slot == (uint32_t)p.nslots) slot = 0, phase ^= 1;
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
     // The whole warp runs the (warp-uniform) control flow so that descriptors live in uniform registers; a single
     // elected lane issues tcgen05.mma / tcgen05.commit.
     const uint32_t w_base = smem_u32(w_s);
-    const uint32_t a_hi = desc_hi(G::ROW * 16);
+    const uint32_t a_hi = desc_hi(G::ROW * RB, kLayoutA);
     const uint32_t b_hi = desc_hi(128);
     // mode 0/1: accumulator block of output plane od = od - o0 (chunk <= R, so the depth-stacked window never wraps:
     // switching the accumulator address between consecutive MMAs costs ~230 cycles, measured with tools/umma_bench.cu).
@@ -368,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
     uint32_t slot = 0, phase = 0;
     long long dbg_tempty = 0, dbg_full = 0, dbg_grp = 0, dbg_t0 = p.dbg ? clock64() : 0;
     int dbg_nst = 0;
-    const uint32_t a_lo0 = desc_lo(smem_u32(slots_s), kChunkStride);
+    const uint32_t a_lo0 = desc_lo(smem_u32(slots_s), 16);
     const uint32_t b_lo0 = desc_lo(w_base, (MODE == 2 ? 1 : 3) * NT * 16);
     uint32_t a_lo = a_lo0;
     if (MODE != 2) {
@@ -424,11 +434,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
         for (int t = t0; t < t0 + 3; ++t) {
           const int th_ = t / 3, tw_ = t % 3;
           // byte offset of the tap's view inside the stage (stride 2: parity sub-plane q, then (kh>>1, kw>>1))
-          const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_) * 16
-                                            : (uint32_t)(((th_ & 1) << 1) | (tw_ & 1)) * (4 * kChunkStride) + (uint32_t)((th_ >> 1) * 9 + (tw_ >> 1)) * 16;
+          const uint32_t voff = (MODE == 0) ? (uint32_t)(th_ * 10 + tw_) * RB
+                                            : (uint32_t)(((th_ & 1) << 1) | (tw_ & 1)) * kBoxStride + (uint32_t)((th_ >> 1) * 9 + (tw_ >> 1)) * RB;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
-            umma_bf16_lh(d1, a_cur + ((ks * 2 * kChunkStride + voff) >> 4), a_hi, b0 + (((uint32_t)(t * 4 + ks * 2) * (3 * NT * 16)) >> 4), b_hi, i1, 1u);
+          for (int ks = 0; ks < KS; ++ks) {
+            // weight slab of this K step: 32-channel half (ks >> 1), 8-channel chunk pair (ks & 1) * 2
+            const uint32_t boff = (uint32_t)(ks >> 1) * (27 * 4 * NT * 16) + (uint32_t)(t * 4 + (ks & 1) * 2) * (3 * NT * 16);
+            umma_bf16_lh(d1, a_cur + ((voff + ks * 32) >> 4), a_hi, b0 + (boff >> 4), b_hi, i1, 1u);
+          }
         }
       };
       // ---- prologue: first stage prepared with blocking waits
@@ -443,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
         // parameters of the CURRENT stage
         const uint32_t i1 = make_idesc((c_ob - c_oa + 1) * NT, FMT);
         const uint32_t d1 = tmem_base + (uint32_t)c_oa * NT;
-        const uint32_t b0 = b_lo0 + (uint32_t)kh * ((27 * 4 * NT * 16) >> 4) + (uint32_t)c_wb * ((NT * 16) >> 4);
+        const uint32_t b0 = b_lo0 + (uint32_t)(kh * (SC / kWHalf)) * ((27 * 4 * NT * 16) >> 4) + (uint32_t)c_wb * ((NT * 16) >> 4);
         const uint32_t a_cur = a_lo, cur_slot = slot;
         const int cur_pl = pl, cur_p1 = p1, cur_o0 = o0, cur_ob = c_ob, cur_nd0 = next_done;
         const bool cur_last_kh = (kh == KH - 1);
@@ -503,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
             const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
             mbar_wait(smem_u32(full_bar + slot), phase);
             tc_fence_after();
-            const uint32_t a0 = desc_lo(smem_u32(slots_s + (size_t)slot * kSlotBytes), kChunkStride);
+            const uint32_t a0 = desc_lo(smem_u32(slots_s + (size_t)slot * kSlotBytes), 16);
             constexpr uint32_t idesc = make_idesc(NT, FMT);
 #pragma unroll 1
             for (int kd = 0; kd < 3; ++kd) {  // oldest output plane first
@@ -520,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
               }
               if (elect_one()) {
                 const uint32_t d_base = tmem_base + set * kSetCols;
-                const uint32_t b0 = desc_lo(w_base + (uint32_t)(kh * 27 + kd * 9) * (4 * NT * 16), NT * 16);
+                const uint32_t b0 = desc_lo(w_base + (uint32_t)(kh * (SC / kWHalf) * 27 + kd * 9) * (4 * NT * 16), NT * 16);
 #pragma unroll
                 for (int cls = 0; cls < 4; ++cls) {
                   const int ph = cls >> 1, pw = cls & 1;
@@ -532,9 +545,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
                       // output parity 0 <- tap 1 (same index); parity 1 <- tap 2 (same index) and tap 0 (index + 1)
                       const int th_ = ph ? (ih ? 0 : 2) : 1, tw_ = pw ? (iw ? 0 : 2) : 1;
 #pragma unroll
-                      for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t a_lo = a0 + ((ks * 2 * kChunkStride + (uint32_t)(ih * 9 + iw) * 16) >> 4);
-                        const uint32_t b_lo = b0 + (((uint32_t)((th_ * 3 + tw_) * 4 + ks * 2) * (NT * 16)) >> 4);
+                      for (int ks = 0; ks < KS; ++ks) {
+                        const uint32_t a_lo = a0 + (((uint32_t)(ih * 9 + iw) * RB + ks * 32) >> 4);
+                        const uint32_t b_lo = b0 + (((uint32_t)(ks >> 1) * (27 * 4 * NT * 16) + (uint32_t)((th_ * 3 + tw_) * 4 + (ks & 1) * 2) * (NT * 16)) >> 4);
                         umma_bf16_lh(d_base + cls * NT, a_lo, a_hi, b_lo, b_hi, idesc, acc);
                         acc = 1u;
                       }
@@ -713,10 +726,10 @@ __global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restric
       for (int k = 0; k < 3; ++k)
         if (wblock_of_kd(mode, k) == blk) kd = k;
     }
-    const int KH = Ci / kStageCh;
+    const int KH = Ci / kWHalf;
     const int kh = (int)(r % KH);
     const int nb = (int)(r / KH);
-    const int co = nb * NT + n, ci = kh * kStageCh + kc * 8 + j, t = kd * 9 + t9;
+    const int co = nb * NT + n, ci = kh * kWHalf + kc * 8 + j, t = kd * 9 + t9;
     float v = 0.f;
     if (co < Co) v = (mode == 2) ? w[((size_t)ci * Co + co) * 27 + t] : w[((size_t)co * Ci + ci) * 27 + t];
     wp[e] = float_to_h16_bits(v, fmt);
@@ -727,7 +740,7 @@ int pick_nt(int Co) { return Co >= 32 ? 32 : 16; }
 
 // 4-D tensor map over the NDHWC activation: dims (C, W, H, B*D), box {8 ch, WV, HV, 1}; stride-2 layers traverse w/h with
 // element stride 2 (one box per parity).  Out-of-bounds elements (halo outside the volume) are zero-filled by the TMA unit.
-int make_tmap(CUtensorMap* tm, const void* x, int fmt, int C, int Wi, int Hi, long long planes, int mode) {
+int make_tmap(CUtensorMap* tm, const void* x, int fmt, int C, int Wi, int Hi, long long planes, int mode, int SC) {
   static decltype(&cuTensorMapEncodeTiled) encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult qres;
@@ -742,15 +755,16 @@ int make_tmap(CUtensorMap* tm, const void* x, int fmt, int C, int Wi, int Hi, lo
   const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wi * C * 2, (cuuint64_t)Hi * Wi * C * 2};
   cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
   if (mode == 0) {
-    box[0] = 8, box[1] = 10, box[2] = 18, box[3] = 1;
+    box[0] = SC, box[1] = 10, box[2] = 18, box[3] = 1;
   } else if (mode == 1) {
-    box[0] = 8, box[1] = 18, box[2] = 34, box[3] = 1;  // ceil(18/2) = 9 columns, ceil(34/2) = 17 rows
+    box[0] = SC, box[1] = 18, box[2] = 34, box[3] = 1;  // ceil(18/2) = 9 columns, ceil(34/2) = 17 rows
     estr[1] = 2, estr[2] = 2;
   } else {
-    box[0] = 8, box[1] = 9, box[2] = 17, box[3] = 1;
+    box[0] = SC, box[1] = 9, box[2] = 17, box[3] = 1;
   }
   const CUresult r = encode(tm, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(x), gdim, gstr, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, SC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("conv3d_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return MODE_ECUDA;
@@ -758,20 +772,24 @@ int make_tmap(CUtensorMap* tm, const void* x, int fmt, int C, int Wi, int Hi, lo
   return MODE_OK;
 }
 
-template <int MODE, int NT, int FMT>
-int launch_tc2(const TcParams& p, const CUtensorMap& tm, int grid, size_t smem, cudaStream_t s) {
+template <int MODE, int NT, int FMT, int SC>
+int launch_tc3(const TcParams& p, const CUtensorMap& tm, int grid, size_t smem, cudaStream_t s) {
   static thread_local size_t attr = 0;
   if (smem > attr) {
-    MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
     attr = smem;
   }
-  conv3d_tc_kernel<MODE, NT, FMT><<<grid, kThreads, smem, s>>>(p, tm);
+  conv3d_tc_kernel<MODE, NT, FMT, SC><<<grid, kThreads, smem, s>>>(p, tm);
   MODE_CHECK_LAUNCH("conv3d_tc");
   return MODE_OK;
 }
+template <int MODE, int NT, int FMT>
+int launch_tc2(const TcParams& p, const CUtensorMap& tm, int sc, int grid, size_t smem, cudaStream_t s) {
+  return sc == 32 ? launch_tc3<MODE, NT, FMT, 32>(p, tm, grid, smem, s) : launch_tc3<MODE, NT, FMT, 64>(p, tm, grid, smem, s);
+}
 template <int MODE, int NT>
-int launch_tc(const TcParams& p, const CUtensorMap& tm, int fmt, int grid, size_t smem, cudaStream_t s) {
-  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, tm, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, tm, grid, smem, s);
+int launch_tc(const TcParams& p, const CUtensorMap& tm, int sc, int fmt, int grid, size_t smem, cudaStream_t s) {
+  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, tm, sc, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, tm, sc, grid, smem, s);
 }
 
 }  // namespace
@@ -787,7 +805,7 @@ extern "C" size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode) {
   (void)mode;
   const int NT = pick_nt(Co);
   const int nblk = (Co + NT - 1) / NT;
-  return (size_t)nblk * (Ci / kStageCh) * 27 * 4 * NT * 8;
+  return (size_t)nblk * (Ci / kWHalf) * 27 * 4 * NT * 8;
 }
 
 extern "C" int mode_conv3d_pack_weights(const float* w, mode_h16* w_packed, int Ci, int Co, int mode, int fmt, void* stream) {
@@ -828,10 +846,12 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   p.tiles_h = ceil_div(th_dim, 16), p.tiles_w = ceil_div(tw_dim, 8);
   p.nblk = ceil_div(Co, NT);
   // shared memory: resident weights + stage ring
-  const int KH = Ci / kStageCh;
-  const size_t w_bytes = ((size_t)KH * 27 * 4 * NT * 16 + 127) & ~(size_t)127;
-  const size_t slot_bytes = (size_t)(mode == 0 ? Geo<0>::NBOX * Geo<0>::BOX_STRIDE : mode == 1 ? Geo<1>::NBOX * Geo<1>::BOX_STRIDE : Geo<2>::NBOX * Geo<2>::BOX_STRIDE);
-  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128;
+  // stage channels: the whole Cin, except stride-2 layers with Cin = 64 (four parity boxes of 128-byte rows would need 80 KB per stage)
+  const int SC = (mode == 1) ? 32 : Ci;
+  const size_t w_bytes = ((size_t)(Ci / kWHalf) * 27 * 4 * NT * 16 + 1023) & ~(size_t)1023;
+  const size_t nvox = (mode == 0) ? Geo<0>::NVOX : Geo<1>::NVOX, nbox = (mode == 1) ? 4 : 1;
+  const size_t slot_bytes = nbox * (((nvox * SC * 2) + 1023) & ~(size_t)1023);
+  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128 + 1024;  // + worst-case alignment of the dynamic smem base
   const size_t budget = 227 * 1024;
   // Two co-resident CTAs per SM when they fit (stride-1 / stride-2 layers with <= 55 KB of weights): the MMA-issuing warp is
   // bound by its own instruction latency (~1700 cycles of waits + bookkeeping + issue per 18-MMA stage against ~1000 cycles of
@@ -862,7 +882,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
     const long long items = cols * nch_eff;
     const long long ctas = std::min<long long>(items, sm_slots / p.nblk);
     const long long rounds = (items + ctas - 1) / ctas;
-    const double stages = (double)(mode == 1 ? 2 * c + halo : c + halo);
+    const double stages = (double)(mode == 1 ? 2 * c + halo : c + halo) * (Ci / SC);
     const double cost = (double)rounds * (stages + 1.5);  // +1.5: per-item pipeline ramp
     if (cost < best - 1e-9) best = cost, best_chunk = c;
   }
@@ -877,16 +897,16 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   cudaStream_t s = (cudaStream_t)stream;
   CUtensorMap tm;
   {
-    const int rc = make_tmap(&tm, x, fmt, Ci, Wi, Hi, (long long)B * Di, mode);
+    const int rc = make_tmap(&tm, x, fmt, Ci, Wi, Hi, (long long)B * Di, mode, SC);
     if (rc != MODE_OK) return rc;
   }
   if (NT == 32) {
-    if (mode == 0) return launch_tc<0, 32>(p, tm, fmt, grid, smem, s);
-    if (mode == 1) return launch_tc<1, 32>(p, tm, fmt, grid, smem, s);
-    return launch_tc<2, 32>(p, tm, fmt, grid, smem, s);
+    if (mode == 0) return launch_tc<0, 32>(p, tm, SC, fmt, grid, smem, s);
+    if (mode == 1) return launch_tc<1, 32>(p, tm, SC, fmt, grid, smem, s);
+    return launch_tc<2, 32>(p, tm, SC, fmt, grid, smem, s);
   }
-  if (mode == 0) return launch_tc<0, 16>(p, tm, fmt, grid, smem, s);
-  if (mode == 1) return launch_tc<1, 16>(p, tm, fmt, grid, smem, s);
+  if (mode == 0) return launch_tc<0, 16>(p, tm, SC, fmt, grid, smem, s);
+  if (mode == 1) return launch_tc<1, 16>(p, tm, SC, fmt, grid, smem, s);
   set_error("conv3d_tc: unsupported configuration");
   return MODE_ENOSUP;
 }
