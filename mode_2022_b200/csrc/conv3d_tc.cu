@@ -32,8 +32,14 @@ using namespace mode;
 
 namespace {
 
-constexpr int kEpiWarps = 4, kProdWarps = 1;
-constexpr int kThreads = (kEpiWarps + 1 + kProdWarps) * 32;  // 192
+// warp roles: [0, EW) epilogue (TMEM lane quadrant = warp & 3), warp EW = MMA issuer, warp EW+1 = TMA producer.
+// Transposed convs write 8x more output voxels than they read and add a same-sized residual: their epilogue is the
+// bottleneck (per-CTA timers: the MMA warp waited 80 % of the time for TMEM blocks), so they get 16 epilogue warps
+// (one per lane quadrant x output parity class) instead of 4.
+template <int MODE>
+constexpr int epi_warps() { return MODE == 2 ? 16 : 4; }
+template <int MODE>
+constexpr int num_threads() { return (epi_warps<MODE>() + 2) * 32; }
 constexpr int kMaxSlots = 8;
 constexpr int kMaxSets = 32;  // TMEM accumulator blocks (512 columns / NT) or sets (transposed conv)
 constexpr int kWHalf = 32;  // the packed weights are organised in 32-input-channel halves
@@ -251,11 +257,14 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
 // ascending OUTPUT plane so that one MMA with N = nb*NT updates nb adjacent TMEM accumulator blocks at once.
 //   mode 0: block = 2 - kd  (kd = 2 -> oldest output plane p-1, kd = 0 -> newest p+1)
 //   mode 1: odd input planes feed kd = 2 (block 0) and kd = 0 (block 1); even planes feed kd = 1 (block 2)
-__host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
+//   mode 2: block = kd (input plane p feeds output planes 2p-1, 2p, 2p+1)
+__host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : mode == 2 ? kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
 
 template <int MODE, int NT, int FMT, int SC>
-__global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<MODE>;
+  constexpr int kEpiWarps = epi_warps<MODE>();
+  constexpr int kThreads = num_threads<MODE>();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle patterns are anchored at 1024-byte boundaries
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
@@ -277,9 +286,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
   // TMEM: mode 0/1 use a ring of R = 512/NT accumulator blocks (one per output plane in flight); mode 2 a ring of 3
   // sets x 4 parity classes.
   constexpr int kSetCols = G::ACCS * NT;
-  const int R = (MODE == 2) ? 3 : p.tmem_cols / NT;
+  const int R = (MODE == 2) ? 4 : p.tmem_cols / NT;  // mode 2: ring of 4 output planes x 4 parity classes x NT columns
   const uint32_t kTmemCols = (uint32_t)p.tmem_cols;
-  static_assert(3 * 4 * NT <= 512 && 512 / NT <= kMaxSets, "TMEM ring overflow");
+  static_assert(4 * 4 * NT <= 512 && 512 / NT <= kMaxSets, "TMEM ring overflow");
 
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
@@ -322,9 +331,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  if (MODE != 2 && warp < kEpiWarps) {
+  if (warp < kEpiWarps) {
     // depth-stacked MMAs always accumulate: every accumulator block starts at zero (and is re-zeroed by the epilogue)
-    for (int c = 0; c < p.tmem_cols; c += 32) tmem_zero<32>(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    for (int c = (warp >> 2) * 32; c < p.tmem_cols; c += 32 * (kEpiWarps / 4)) tmem_zero<32>(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + c);
     tmem_st_wait();
   }
   tc_fence_before();
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
     long long dbg_tempty = 0, dbg_full = 0, dbg_grp = 0, dbg_t0 = p.dbg ? clock64() : 0;
     int dbg_nst = 0;
     const uint32_t a_lo0 = desc_lo(smem_u32(slots_s), 16);
-    const uint32_t b_lo0 = desc_lo(w_base, (MODE == 2 ? 1 : 3) * NT * 16);
+    const uint32_t b_lo0 = desc_lo(w_base, 3 * NT * 16);
     uint32_t a_lo = a_lo0;
     if (MODE != 2) {
       // ---- depth-stacked issue, software pipelined.  One stage = (input plane, 32-channel half) = 18 MMAs (9 in-plane taps x
@@ -511,56 +520,66 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
       chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
       for (int pl = p0; pl <= p1; ++pl) {
         {
-          // ---- transposed conv: per output plane a set of 4 parity-class accumulators
-          for (int kh = 0; kh < KH; ++kh, ++stage) {
-            const uint32_t slot = stage % p.nslots, phase = (stage / p.nslots) & 1;
-            mbar_wait(smem_u32(full_bar + slot), phase);
-            tc_fence_after();
-            const uint32_t a0 = desc_lo(smem_u32(slots_s + (size_t)slot * kSlotBytes), 16);
-            constexpr uint32_t idesc = make_idesc(NT, FMT);
-#pragma unroll 1
-            for (int kd = 0; kd < 3; ++kd) {  // oldest output plane first
-              const int od = 2 * pl - 1 + kd;
-              if (od < o0 || od >= o1) continue;
-              int first, last;
-              contrib_range<MODE>(p, od, first, last);
+          // ---- transposed conv, depth-stacked: accumulator block of (parity class c, output plane od) sits at TMEM column
+          // (c*4 + job%4)*NT, so for a fixed class the <= 3 output planes fed by this input plane (kd = 0,1,2 -> od = 2p-1,
+          // 2p, 2p+1) are adjacent column blocks and one MMA with N = nb*NT updates them all (two MMAs when the ring of 4
+          // wraps).  9 (class, in-plane shift) views x KS K-steps = 36..72 MMAs per plane instead of 108 N=32 ones.
+          const uint32_t slot_ = stage % p.nslots, phase_ = (stage / p.nslots) & 1;
+          ++stage;
+          const int od_lo = max(2 * pl - 1, o0), od_hi = min(2 * pl + 1, o1 - 1);
+          const int nb = od_hi - od_lo + 1, kd_a = od_lo - (2 * pl - 1);
+          const uint32_t ja = job_base + (uint32_t)(od_lo - o0);
+          const uint32_t ca = ja % 4;
+          const int n1 = min(nb, (int)(4 - ca)), n2 = nb - n1;
+          long long c0 = p.dbg ? clock64() : 0;
+          for (int od = od_lo; od <= od_hi; ++od) {  // first touch: the epilogue must have drained + zeroed the 4 class blocks
+            int first, last;
+            contrib_range<MODE>(p, od, first, last);
+            if (first == pl) {
               const uint32_t job = job_base + (uint32_t)(od - o0);
-              const uint32_t set = job % R;
-              const bool fresh = (pl == first && kh == 0);
-              if (fresh) {
-                mbar_wait(smem_u32(tempty_bar + set), ((job / R) & 1) ^ 1);
-                tc_fence_after();
-              }
-              if (elect_one()) {
-                const uint32_t d_base = tmem_base + set * kSetCols;
-                const uint32_t b0 = desc_lo(w_base + (uint32_t)(kh * (SC / kWHalf) * 27 + kd * 9) * (4 * NT * 16), NT * 16);
+              mbar_wait(smem_u32(tempty_bar + job % 4), ((job / 4) & 1) ^ 1);
+            }
+          }
+          if (p.dbg) dbg_tempty += clock64() - c0;
+          c0 = p.dbg ? clock64() : 0;
+          mbar_wait(smem_u32(full_bar + slot_), phase_);
+          if (p.dbg) dbg_full += clock64() - c0;
+          tc_fence_after();
+          c0 = p.dbg ? clock64() : 0;
+          if (nb > 0 && elect_one()) {
+            const uint32_t a0 = desc_lo(smem_u32(slots_s + (size_t)slot_ * kSlotBytes), 16);
+            const uint32_t b0 = b_lo0 + (uint32_t)kd_a * ((NT * 16) >> 4);
+            const uint32_t i1 = make_idesc(n1 * NT, FMT), i2 = make_idesc(max(n2, 1) * NT, FMT);
 #pragma unroll
-                for (int cls = 0; cls < 4; ++cls) {
-                  const int ph = cls >> 1, pw = cls & 1;
-                  uint32_t acc = fresh ? 0u : 1u;
+            for (int cls = 0; cls < 4; ++cls) {
+              const int ph = cls >> 1, pw = cls & 1;
+              const uint32_t d1 = tmem_base + (uint32_t)(cls * 4 + ca) * NT, d2 = tmem_base + (uint32_t)(cls * 4) * NT;
 #pragma unroll
-                  for (int ih = 0; ih <= ph; ++ih) {
+              for (int ih = 0; ih <= ph; ++ih) {
 #pragma unroll
-                    for (int iw = 0; iw <= pw; ++iw) {
-                      // output parity 0 <- tap 1 (same index); parity 1 <- tap 2 (same index) and tap 0 (index + 1)
-                      const int th_ = ph ? (ih ? 0 : 2) : 1, tw_ = pw ? (iw ? 0 : 2) : 1;
+                for (int iw = 0; iw <= pw; ++iw) {
+                  // output parity 0 <- tap 1 (same index); parity 1 <- tap 2 (same index) and tap 0 (index + 1)
+                  const int th_ = ph ? (ih ? 0 : 2) : 1, tw_ = pw ? (iw ? 0 : 2) : 1;
 #pragma unroll
-                      for (int ks = 0; ks < KS; ++ks) {
-                        const uint32_t a_lo = a0 + (((uint32_t)(ih * 9 + iw) * RB + ks * 32) >> 4);
-                        const uint32_t b_lo = b0 + (((uint32_t)(ks >> 1) * (27 * 4 * NT * 16) + (uint32_t)((th_ * 3 + tw_) * 4 + (ks & 1) * 2) * (NT * 16)) >> 4);
-                        umma_bf16_lh(d_base + cls * NT, a_lo, a_hi, b_lo, b_hi, idesc, acc);
-                        acc = 1u;
-                      }
-                    }
+                  for (int ks = 0; ks < KS; ++ks) {
+                    const uint32_t a_lo = a0 + (((uint32_t)(ih * 9 + iw) * RB + ks * 32) >> 4);
+                    const uint32_t b_lo = b0 + (((uint32_t)(ks >> 1) * (27 * 4 * NT * 16) + (uint32_t)((th_ * 3 + tw_) * 4 + (ks & 1) * 2) * (3 * NT * 16)) >> 4);
+                    umma_bf16_lh(d1, a_lo, a_hi, b_lo, b_hi, i1, 1u);
+                    if (n2 > 0) umma_bf16_lh(d2, a_lo, a_hi, b_lo + (((uint32_t)n1 * NT * 16) >> 4), b_hi, i2, 1u);
                   }
                 }
-                if (pl == last && kh == KH - 1) umma_commit(smem_u32(tfull_bar + set));
               }
-              __syncwarp();
             }
-            if (elect_one()) umma_commit(smem_u32(empty_bar + slot));
-            __syncwarp();
+            for (int od = od_lo; od <= od_hi; ++od) {
+              int first, last;
+              contrib_range<MODE>(p, od, first, last);
+              if (last == pl) umma_commit(smem_u32(tfull_bar + (job_base + (uint32_t)(od - o0)) % 4));  // all 4 class blocks complete
+            }
           }
+          __syncwarp();
+          if (elect_one()) umma_commit(smem_u32(empty_bar + slot_));
+          __syncwarp();
+          if (p.dbg) dbg_grp += clock64() - c0;
         }
       }
       job_base += (uint32_t)(o1 - o0);
@@ -574,7 +593,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
     }
   } else {
     // =========================================================== EPILOGUE (4 warps = 128 rows)
-    const int row = warp * 32 + lane;  // TMEM lane == GEMM row == tile position
+    const int row = (warp & 3) * 32 + lane;  // TMEM lane == GEMM row == tile position
+    const int cls = (MODE == 2) ? (warp >> 2) : 0;  // transposed conv: this warp's output parity class
     const int hl = row >> 3, wl = row & 7;
     uint32_t job_base = 0, use_mask = 0;
     long long dbg_tfull = 0;
@@ -592,32 +612,36 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
         } else {
           set = job % R, par = (job / R) & 1;
         }
+        // this warp's output voxel; residual operands do not depend on the accumulator: fetch them BEFORE waiting for it
+        int oh, ow;
+        bool ok;
+        if (MODE == 2) {
+          const int ih = it.th * 16 + hl, iw = it.tw * 8 + wl;
+          oh = 2 * ih + (cls >> 1), ow = 2 * iw + (cls & 1);
+          ok = ih < p.Hi && iw < p.Wi;
+        } else {
+          oh = it.th * 16 + hl, ow = it.tw * 8 + wl;
+          ok = oh < p.Ho && ow < p.Wo;
+        }
+        const size_t vox = (((size_t)it.b * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+        uint4 rpre[NT / 8];
+        const float rpre_f32 = (ok && p.res_f32) ? __ldg(p.res_f32 + vox * p.CoReal) : 0.f;
+#pragma unroll
+        for (int q = 0; q < NT / 8; ++q) rpre[q] = (ok && p.res) ? ld_nc_v4(p.res + vox * p.Co + n0 + q * 8) : make_uint4(0, 0, 0, 0);
         const long long e0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(tfull_bar + set), par);
         if (p.dbg) dbg_tfull += clock64() - e0;
         tc_fence_after();
-#pragma unroll 1
-        for (int cls = 0; cls < G::ACCS; ++cls) {
+        {
           uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + set * kSetCols + cls * NT;
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (MODE == 2 ? (uint32_t)(cls * 4 + set) * NT : set * NT);
           if (NT == 32)
             tmem_ld32(taddr, v);
           else
             tmem_ld16(taddr, v);
           tmem_ld_wait();
-          if (MODE != 2) tmem_zero<NT>(taddr);  // hand the block back zeroed (completion awaited below)
-          int oh, ow;
-          bool ok;
-          if (MODE == 2) {
-            const int ih = it.th * 16 + hl, iw = it.tw * 8 + wl;
-            oh = 2 * ih + (cls >> 1), ow = 2 * iw + (cls & 1);
-            ok = ih < p.Hi && iw < p.Wi;
-          } else {
-            oh = it.th * 16 + hl, ow = it.tw * 8 + wl;
-            ok = oh < p.Ho && ow < p.Wo;
-          }
+          tmem_zero<NT>(taddr);  // hand the block back zeroed (completion awaited below)
           if (ok) {
-            const size_t vox = (((size_t)it.b * p.Do + od) * p.Ho + oh) * p.Wo + ow;
             if (p.out_f32 != nullptr) {
               // classifier: only the first CoReal (=1) channels are real
 #pragma unroll
@@ -626,12 +650,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
                 float y = __uint_as_float(v[c]);
                 if (p.scale) y *= __ldg(p.scale + c);
                 if (p.shift) y += __ldg(p.shift + c);
-                if (p.res_f32) y += __ldg(p.res_f32 + vox * p.CoReal + c);
+                if (p.res_f32) y += (c == 0) ? rpre_f32 : __ldg(p.res_f32 + vox * p.CoReal + c);
                 if (p.relu) y = fmaxf(y, 0.f);
                 p.out_f32[vox * p.CoReal + c] = y;
               }
             } else {
-              const uint16_t* rp = p.res ? p.res + vox * p.Co + n0 : nullptr;
               uint16_t* op = p.out + vox * p.Co + n0;
 #pragma unroll
               for (int q = 0; q < NT / 8; ++q) {
@@ -648,8 +671,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
                   const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q * 8) + 1);
                   y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
                 }
-                if (rp) {
-                  const uint4 r = ld_nc_v4(rp + q * 8);
+                if (p.res) {
+                  const uint4 r = rpre[q];
                   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
@@ -669,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv3d_tc_kernel(const TcParams p
             }
           }
         }
-        if (MODE != 2) tmem_st_wait();
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(tempty_bar + set));
@@ -709,13 +732,7 @@ __global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restric
     const int n = (int)(r % NT);
     r /= NT;
     int kd, t9, kc;
-    if (mode == 2) {
-      kc = (int)(r % 4);
-      r /= 4;
-      const int t = (int)(r % 27);
-      r /= 27;
-      kd = t / 9, t9 = t % 9;
-    } else {
+    {
       const int blk = (int)(r % 3);
       r /= 3;
       kc = (int)(r % 4);
@@ -779,7 +796,7 @@ int launch_tc3(const TcParams& p, const CUtensorMap& tm, int grid, size_t smem, 
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
     attr = smem;
   }
-  conv3d_tc_kernel<MODE, NT, FMT, SC><<<grid, kThreads, smem, s>>>(p, tm);
+  conv3d_tc_kernel<MODE, NT, FMT, SC><<<grid, num_threads<MODE>(), smem, s>>>(p, tm);
   MODE_CHECK_LAUNCH("conv3d_tc");
   return MODE_OK;
 }

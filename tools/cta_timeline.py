@@ -6,15 +6,20 @@ from mode_2022_b200 import ops, _lib
 lib = _lib.load()
 dev = 'cuda'
 ci, co, dims, mode = [int(v) for v in os.environ.get('CFG', '32,32,48,256,128,0').split(',')][:2] + [tuple(int(v) for v in os.environ.get('CFG', '32,32,48,256,128,0').split(',')[2:5])] + [int(os.environ.get('CFG', '32,32,48,256,128,0').split(',')[5])]
-x = torch.randn(1, *dims, ci, device=dev).bfloat16()
+B = int(os.environ.get('BATCH', '1'))
+x = torch.randn(B, *dims, ci, device=dev).bfloat16()
+res = None
+if os.environ.get('RES'):
+  od = ops.conv3d_out_dims(*dims, mode)
+  res = torch.randn(B, *od, co, device=dev).bfloat16()
 w = torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), device=dev) / math.sqrt(27 * ci)
 wp = ops.conv3d_pack_weights(w, mode)
 for _ in range(3):
-  ops.conv3d_bf16(x, wp, co, None, None, None, mode, True, False)
+  ops.conv3d_bf16(x, wp, co, None, None, res, mode, True, False)
 dbg = torch.zeros(148 * 8 + 4 * 64, dtype=torch.int64, device=dev)
 lib.mode_conv3d_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
 torch.cuda.synchronize()
-ops.conv3d_bf16(x, wp, co, None, None, None, mode, True, False)
+ops.conv3d_bf16(x, wp, co, None, None, res, mode, True, False)
 torch.cuda.synchronize()
 lib.mode_conv3d_set_debug_buffer(ctypes.c_void_p(0))
 st = dbg[148 * 8:].view(4, 64).cpu()
