@@ -293,7 +293,10 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
   uint8_t* slots_s = smem + ((w_bytes + 1023) & ~1023u);  // swizzled boxes: 1024-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slots_s + (size_t)p.nslots * kSlotBytes);
+  // transposed conv: per-warp 2 KB + 2 KB staging tiles (residual in / output out) used to turn the row-per-thread epilogue
+  // accesses (64 B per thread at a 128 B stride = 32 L1 wavefronts per instruction) into lane-contiguous ones
+  uint8_t* epi_s = slots_s + (size_t)p.nslots * kSlotBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_s + (MODE == 2 ? kEpiWarps * 4096 : 0));
   uint64_t* full_bar = bars;                               // [nslots] producers -> MMA
   uint64_t* empty_bar = bars + kMaxSlots;                  // [nslots] MMA (commit) -> producers
   uint64_t* tfull_bar = bars + 2 * kMaxSlots;              // [R]      MMA (commit) -> epilogue
@@ -626,8 +629,36 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
         const size_t vox = (((size_t)it.b * p.Do + od) * p.Ho + oh) * p.Wo + ow;
         uint4 rpre[NT / 8];
         const float rpre_f32 = (ok && p.res_f32) ? __ldg(p.res_f32 + vox * p.CoReal) : 0.f;
+        // lane-contiguous view of this warp's 32 rows x 64 B: instruction k, lane t <-> row 8k + (t >> 2), 16-byte chunk t & 3
+        uint8_t* tile_res = epi_s + (size_t)warp * 4096;
+        uint8_t* tile_out = tile_res + 2048;
+        size_t vox_c[4];
+        bool ok_c[4];
+        if (MODE == 2 && NT == 32) {
 #pragma unroll
-        for (int q = 0; q < NT / 8; ++q) rpre[q] = (ok && p.res) ? ld_nc_v4(p.res + vox * p.Co + n0 + q * 8) : make_uint4(0, 0, 0, 0);
+          for (int k = 0; k < 4; ++k) {
+            const int ih = it.th * 16 + (warp & 3) * 4 + k, iw = it.tw * 8 + (lane >> 2);
+            ok_c[k] = ih < p.Hi && iw < p.Wi;
+            vox_c[k] = (((size_t)it.b * p.Do + od) * p.Ho + (2 * ih + (cls >> 1))) * p.Wo + (2 * iw + (cls & 1));
+          }
+          __syncwarp();  // previous job's reads of the staging tiles are done
+          if (p.res) {
+            uint4 rc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rc[k] = ok_c[k] ? ld_nc_v4(p.res + vox_c[k] * p.Co + n0 + (lane & 3) * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int r = 8 * k + (lane >> 2);
+              *reinterpret_cast<uint4*>(tile_res + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4)) = rc[k];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rpre[q] = *reinterpret_cast<const uint4*>(tile_res + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NT / 8; ++q) rpre[q] = (ok && p.res) ? ld_nc_v4(p.res + vox * p.Co + n0 + q * 8) : make_uint4(0, 0, 0, 0);
+        }
         const long long e0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(tfull_bar + set), par);
         if (p.dbg) dbg_tfull += clock64() - e0;
@@ -687,9 +718,21 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
                 }
                 uint4 o;
                 o.x = pack2<FMT>(y[0], y[1]), o.y = pack2<FMT>(y[2], y[3]), o.z = pack2<FMT>(y[4], y[5]), o.w = pack2<FMT>(y[6], y[7]);
-                *reinterpret_cast<uint4*>(op + q * 8) = o;
+                if (MODE == 2 && NT == 32)
+                  *reinterpret_cast<uint4*>(tile_out + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;  // staged, stored below
+                else
+                  *reinterpret_cast<uint4*>(op + q * 8) = o;
               }
             }
+          }
+        }
+        if (MODE == 2 && NT == 32 && p.out_f32 == nullptr) {
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = 8 * k + (lane >> 2);
+            const uint4 o = *reinterpret_cast<const uint4*>(tile_out + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
+            if (ok_c[k]) *reinterpret_cast<uint4*>(p.out + vox_c[k] * p.Co + n0 + (lane & 3) * 8) = o;
           }
         }
         tmem_st_wait();
@@ -868,7 +911,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   const size_t w_bytes = ((size_t)(Ci / kWHalf) * 27 * 4 * NT * 16 + 1023) & ~(size_t)1023;
   const size_t nvox = (mode == 0) ? Geo<0>::NVOX : Geo<1>::NVOX, nbox = (mode == 1) ? 4 : 1;
   const size_t slot_bytes = nbox * (((nvox * SC * 2) + 1023) & ~(size_t)1023);
-  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128 + 1024;  // + worst-case alignment of the dynamic smem base
+  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128 + 1024 + (mode == 2 ? 16 * 4096 : 0);  // barriers, smem base alignment, epilogue staging
   const size_t budget = 227 * 1024;
   // Two co-resident CTAs per SM when they fit (stride-1 / stride-2 layers with <= 55 KB of weights): the MMA-issuing warp is
   // bound by its own instruction latency (~1700 cycles of waits + bookkeeping + issue per 18-MMA stage against ~1000 cycles of
