@@ -65,10 +65,12 @@ int mode_sphere_conv_f32(const float* x, const float* pos, const float* w, const
                          const float* residual, float* out, int B, int C, int H, int W, int Co, int Kh, int Kw, int relu, void* stream);
 /* tensor-core (tcgen05) variant: x (B,H,W,C) NHWC 16-bit, w_packed from mode_sphere_conv_pack_weights,
  * out (B,H,W,Co) 16-bit, fp32 accumulation.  C % 64 == 0, Co in {64,128,192,256}, 3x3. */
-/* gather table = the sampling grid pre-digested once per resolution: per (tap, pixel) four corner pixel indices (-1 =
- * dropped by the reference's edge rules) + four bilinear weights; mode_sphere_conv_table_bytes() bytes, caller-allocated. */
+/* gather table = the sampling grid pre-digested once per resolution and 16-bit format (fmt = MODE_FMT_*): per (tap,
+ * pixel) the top-left corner's pixel index + the four bilinear weights in that format (0 where the reference's edge rules
+ * drop the corner); mode_sphere_conv_table_bytes() bytes, caller-allocated.  The table passed to mode_sphere_conv_tc must
+ * have been built with the same fmt. */
 size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw);
-int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, void* stream);
+int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, int fmt, void* stream);
 int mode_sphere_conv_tc(const mode_h16* x, const void* table, const mode_h16* w_packed, const float* scale, const float* shift,
                         const mode_h16* residual, mode_h16* out, int B, int C, int H, int W, int Co, int relu, int fmt, void* stream);
 int mode_sphere_conv_pack_weights(const float* w /*Co,C,3,3*/, mode_h16* w_packed, int C, int Co, int fmt, void* stream);

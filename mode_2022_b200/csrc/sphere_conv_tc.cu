@@ -17,6 +17,9 @@
 // The kernel is gather-bound, not MMA-bound: per 128-pixel tile the corner loads alone are 128 x 9 x 4 x 256 B =
 // 1.18 MB of L1 traffic (~9.2k wavefront cycles) against 4.6k MMA cycles.  One CTA (16 gather warps) per SM with a
 // minimal shared-memory carve-out, so that the tile's ~45 KB input neighbourhood stays L1 resident across the 36 re-reads.
+#include <cuda.h>
+#include <string.h>
+
 #include "common.cuh"
 using namespace mode;
 
@@ -29,28 +32,37 @@ constexpr int kChunkStrideA = 128 * 16 + 16;             // 2064 B: +16 B pad ->
 constexpr int kABytes = ((8 * kChunkStrideA) + 127) & ~127;  // 16640
 
 // packed 16-bit blend: r = w1*v1 + w2*v2 + w3*v3 + w4*v4 on two channels at once (HFMA2.BF16 / HFMA2): 4 instructions per
-// channel pair instead of 2 unpacks + 8 FFMAs + a pack.  The gather is instruction-issue bound (ncu: IPC 2.0, tensor pipe
-// 8 % active), so this is the lever; the price is that the partial sums are rounded to the storage format.
+// channel pair instead of 2 unpacks + 8 FFMAs + a pack; the price is that the partial sums are rounded to the storage
+// format.  w12 = (w1, w2), w34 = (w3, w4) as 16-bit pairs: the broadcasts fold into HFMA2 operand selectors (.H0_H0 / .H1_H1).
 template <int FMT>
-__device__ __forceinline__ uint32_t blend2(uint32_t w1, uint32_t v1, uint32_t w2, uint32_t v2, uint32_t w3, uint32_t v3, uint32_t w4, uint32_t v4) {
+__device__ __forceinline__ uint32_t blend2(uint32_t w12, uint32_t w34, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4) {
   if (FMT == kFmtBF16) {
-    const __nv_bfloat162 r = __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w4), *reinterpret_cast<__nv_bfloat162*>(&v4),
-                             __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w3), *reinterpret_cast<__nv_bfloat162*>(&v3),
-                             __hfma2(*reinterpret_cast<__nv_bfloat162*>(&w2), *reinterpret_cast<__nv_bfloat162*>(&v2),
-                             __hmul2(*reinterpret_cast<__nv_bfloat162*>(&w1), *reinterpret_cast<__nv_bfloat162*>(&v1)))));
+    const __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&w12), b = *reinterpret_cast<__nv_bfloat162*>(&w34);
+    const __nv_bfloat162 r = __hfma2(__high2bfloat162(b), *reinterpret_cast<__nv_bfloat162*>(&v4),
+                             __hfma2(__low2bfloat162(b), *reinterpret_cast<__nv_bfloat162*>(&v3),
+                             __hfma2(__high2bfloat162(a), *reinterpret_cast<__nv_bfloat162*>(&v2),
+                             __hmul2(__low2bfloat162(a), *reinterpret_cast<__nv_bfloat162*>(&v1)))));
     return *reinterpret_cast<const uint32_t*>(&r);
   } else {
-    const __half2 r = __hfma2(*reinterpret_cast<__half2*>(&w4), *reinterpret_cast<__half2*>(&v4),
-                      __hfma2(*reinterpret_cast<__half2*>(&w3), *reinterpret_cast<__half2*>(&v3),
-                      __hfma2(*reinterpret_cast<__half2*>(&w2), *reinterpret_cast<__half2*>(&v2),
-                      __hmul2(*reinterpret_cast<__half2*>(&w1), *reinterpret_cast<__half2*>(&v1)))));
+    const __half2 a = *reinterpret_cast<__half2*>(&w12), b = *reinterpret_cast<__half2*>(&w34);
+    const __half2 r = __hfma2(__high2half2(b), *reinterpret_cast<__half2*>(&v4),
+                      __hfma2(__low2half2(b), *reinterpret_cast<__half2*>(&v3),
+                      __hfma2(__high2half2(a), *reinterpret_cast<__half2*>(&v2),
+                      __hmul2(__low2half2(a), *reinterpret_cast<__half2*>(&v1)))));
     return *reinterpret_cast<const uint32_t*>(&r);
   }
 }
 
+// 16-byte read-only load executed only when `take` != 0; otherwise v keeps its previous (finite) contents
+__device__ __forceinline__ void ldg_if(uint4& v, const void* ptr, uint32_t take) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
+               : "l"(ptr), "r"(take));
+}
+
 struct ScParams {
   const uint16_t* x;    // (B,H,W,C) bf16
-  const int4* table;    // [9][H*W] x {int4 corner pixel index (-1 = dropped), float4 bilinear weight}: built once per grid
+  const int4* table;    // [9][H*W] x {top-left corner pixel index, w1|w2, w3|w4 (16-bit, storage format), 0}: built once per grid and format
   const uint16_t* wpk;  // [9][C/64][8][Co][8] bf16
   const float* scale;
   const float* shift;
@@ -60,6 +72,7 @@ struct ScParams {
   long long npix;       // B*H*W
   int ntiles;
   int tw, th, tiles_x, tiles_y;  // tile = th x tw pixels (th*tw == 128); tw == 0: linear tiles of 128 consecutive pixels
+  int epi_tma;                   // epilogue moves the residual / output tiles with TMA (2-D tiles, Co/ngrp == 32)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,28 +140,35 @@ __device__ __forceinline__ long long tile_pixel(const ScParams& p, int tile, int
   return (long long)b * HW + (long long)y * p.W + x;
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScParams p) {
+// CC: compile-time channel count (128 = the model's layer4; 0 = read it from the parameters)
+template <int FMT, int CC>
+__global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScParams p, const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t b_bytes = (uint32_t)p.Co * 64 * 2;          // one weight slab: Co x 64 ch
   const uint32_t stage_bytes = kABytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStagesS * stage_bytes);
+  // per-warp 2 KB epilogue tile (32 pixels x 32 channels, 64-byte-swizzled): residual in (TMA load), output out (TMA store)
+  uint8_t* epi_s = smem + (((size_t)kStagesS * stage_bytes + 1023) & ~(size_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_s + kGatherWarps * 2048);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStagesS;
-  uint64_t* tfull_bar = bars + 2 * kStagesS;
-  uint64_t* tempty_bar = bars + 2 * kStagesS + 1;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStagesS + 2);
-  const int tmem_cols = p.Co <= 32 ? 32 : p.Co <= 64 ? 64 : p.Co <= 128 ? 128 : 256;
+  uint64_t* tfull_bar = bars + 2 * kStagesS;       // [2]: the accumulator is double buffered
+  uint64_t* tempty_bar = bars + 2 * kStagesS + 2;  // [2]
+  uint64_t* res_bar = bars + 2 * kStagesS + 4;     // [kGatherWarps]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kStagesS + 4 + kGatherWarps);
+  const int tmem_cols = p.Co <= 16 ? 32 : p.Co <= 32 ? 64 : p.Co <= 64 ? 128 : p.Co <= 128 ? 256 : 512;  // 2 accumulators
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStagesS; ++i) {
       mbar_init(smem_u32(full_bar + i), kGatherWarps + 1);  // 16 gather warps + the weight loader's expect_tx arrive
       mbar_init(smem_u32(empty_bar + i), 1);
     }
-    mbar_init(smem_u32(tfull_bar), 1);
-    mbar_init(smem_u32(tempty_bar), kGatherWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(tfull_bar + i), 1);
+      mbar_init(smem_u32(tempty_bar + i), kGatherWarps);
+    }
+    for (int i = 0; i < kGatherWarps; ++i) mbar_init(smem_u32(res_bar + i), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kGatherWarps) {
@@ -160,7 +180,8 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   const int HW = p.H * p.W;
-  const int nhalf = p.C / 64;
+  const int C = CC ? CC : p.C;
+  const int nhalf = C / 64;
   const int nstage_tile = 9 * nhalf;
   // contiguous tile ranges per CTA: consecutive tiles are consecutive image rows and share 2 of their 3 input rows in L1
   const int tiles_per = (p.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -171,86 +192,39 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
     const int tid = threadIdx.x;  // 0..511
     const int kc = tid & 7;       // 8-channel chunk inside the 64-channel half
     uint32_t stage = 0, tile_n = 0;
-    for (int tile = tile0; tile < tile1; ++tile, ++tile_n) {
-      // this thread's two pixels of the tile
-      int pp[2];
-      uint32_t base[2];
-      bool inb[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const long long gp = tile_pixel(p, tile, (tid >> 3) + 64 * j, HW);
-        inb[j] = gp >= 0;
-        const int b = inb[j] ? (int)(gp / HW) : 0;
-        pp[j] = inb[j] ? (int)(gp - (long long)b * HW) : 0;
-        base[j] = (uint32_t)b * (uint32_t)HW;
-      }
-      // Stage order is HALF-major (all 9 taps of channels 0..63, then of 64..127): the 36 corner reads of a phase then
-      // touch only ~3 image rows x 128 B per pixel (~50 KB), which stays L1 resident; tap-major order alternated between the
-      // two halves and thrashed the ~120 KB L1 (ncu: 44 % hit rate).  Table entries of the next stage are prefetched.
-      int4 ixn[2];
-      float4 wtn[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        ixn[j] = __ldg(p.table + 2 * ((size_t)0 * HW + pp[j]));
-        wtn[j] = __ldg(reinterpret_cast<const float4*>(p.table + 2 * ((size_t)0 * HW + pp[j]) + 1));
-      }
-      for (int s = 0; s < nstage_tile; ++s, ++stage) {
-        const int half = s / 9, k = s - half * 9;
-        uint32_t w1[2], w2[2], w3[2], w4[2];  // bilinear weights, duplicated into both 16-bit halves
-        uint4 v1[2], v2[2], v3[2], v4[2];
-        const uint32_t coff = (uint32_t)(half * 64 + kc * 8);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {  // all 8 corner loads in flight before the first use
-          const float m = inb[j] ? 1.f : 0.f;
-          w1[j] = pack2<FMT>(wtn[j].x * m, wtn[j].x * m), w2[j] = pack2<FMT>(wtn[j].y * m, wtn[j].y * m);
-          w3[j] = pack2<FMT>(wtn[j].z * m, wtn[j].z * m), w4[j] = pack2<FMT>(wtn[j].w * m, wtn[j].w * m);
-          v1[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)((base[j] + (uint32_t)ixn[j].x) * (uint32_t)p.C + coff)));
-          v2[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)((base[j] + (uint32_t)ixn[j].y) * (uint32_t)p.C + coff)));
-          v3[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)((base[j] + (uint32_t)ixn[j].z) * (uint32_t)p.C + coff)));
-          v4[j] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)((base[j] + (uint32_t)ixn[j].w) * (uint32_t)p.C + coff)));
-        }
-        if (s + 1 < nstage_tile) {  // prefetch the next stage's table entries (in flight during the blend)
-          const int kn = (s + 1) % 9;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            ixn[j] = __ldg(p.table + 2 * ((size_t)kn * HW + pp[j]));
-            wtn[j] = __ldg(reinterpret_cast<const float4*>(p.table + 2 * ((size_t)kn * HW + pp[j]) + 1));
-          }
-        }
-        {
-          const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
-          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
-          uint8_t* a_s = smem + (size_t)slot * stage_bytes;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 o;
-            o.x = blend2<FMT>(w1[j], v1[j].x, w2[j], v2[j].x, w3[j], v3[j].x, w4[j], v4[j].x);
-            o.y = blend2<FMT>(w1[j], v1[j].y, w2[j], v2[j].y, w3[j], v3[j].y, w4[j], v4[j].y);
-            o.z = blend2<FMT>(w1[j], v1[j].z, w2[j], v2[j].z, w3[j], v3[j].z, w4[j], v4[j].z);
-            o.w = blend2<FMT>(w1[j], v1[j].w, w2[j], v2[j].w, w3[j], v3[j].w, w4[j], v4[j].w);
-            const int pix_l = (tid >> 3) + 64 * j;
-            *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = o;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
-        }
-      }
-      // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., column group w/4 of ngrp (4 groups when Co % 128 == 0, else 2)
-      mbar_wait(smem_u32(tfull_bar), tile_n & 1);
+    const int ngrp = (p.Co % 128 == 0) ? 4 : 2;
+    const int q = warp & 3, grp = warp >> 2;
+    uint8_t* etile = epi_s + (size_t)warp * 2048;
+    // TMA coordinates of this warp's 2 x 16 pixel x 32 channel piece of a tile
+    auto epi_coords = [&](int tile, int& cx, int& cy) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      const int b = tile / per_img, t = tile - b * per_img;
+      const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+      cx = tx * 16, cy = b * p.H + ty * 8 + 2 * q;
+    };
+    // ---- epilogue of one tile: warp w reads TMEM lanes 32*(w%4).., column group w/4 of ngrp (4 groups when Co % 128 == 0,
+    // else 2).  It runs one stage into the NEXT tile's gather (the accumulator is double buffered), so the tensor pipe's
+    // tail and the epilogue's own latency hide behind gather work instead of idling the L1 pipe at every tile boundary.
+    // With 2-D tiles the residual piece arrives by TMA and the output piece leaves by TMA through a 64-byte-swizzled 2 KB
+    // tile per warp: row-per-thread global accesses (16 B at a 256 B stride = 32 L1 wavefronts per instruction) would
+    // spend a fifth of the L1 data pipe -- the kernel's bound -- on the epilogue.
+    auto epilogue = [&](int tile, uint32_t tn) {
+      const uint32_t buf = tn & 1;
+      mbar_wait(smem_u32(tfull_bar + buf), (tn >> 1) & 1);
       tc_fence_after();
-      const int ngrp = (p.Co % 128 == 0) ? 4 : 2;
-      const int q = warp & 3, grp = warp >> 2;
-      const long long gp = tile_pixel(p, tile, q * 32 + lane, HW);
-      for (int c0 = grp * (p.Co / ngrp); grp < ngrp && c0 < (grp + 1) * (p.Co / ngrp); c0 += 32) {
+      const uint32_t tacc = tmem_base + buf * (uint32_t)p.Co + ((uint32_t)(q * 32) << 16);
+      const long long gp = p.epi_tma ? 0 : tile_pixel(p, tile, q * 32 + lane, HW);
+      for (int c0 = grp * (p.Co / ngrp); grp < ngrp && c0 < (grp + 1) * (p.Co / ngrp); c0 += 32) {  // exactly one pass when epi_tma
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld32(tacc + c0, v);
+        if (p.epi_tma && p.res) mbar_wait(smem_u32(res_bar + warp), tn & 1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (gp >= 0) {
           const uint16_t* rp = p.res ? p.res + gp * p.Co + c0 : nullptr;
           uint16_t* op = p.out + gp * p.Co + c0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
+            uint8_t* ep = etile + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
             float y[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[g * 8 + e]);
@@ -262,13 +236,13 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
               const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + g * 8) + 1);
               y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
             }
-            if (rp) {
-              const uint4 r = ld_nc_v4(rp + g * 8);
-              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            if (p.res) {
+              const uint4 r = p.epi_tma ? *reinterpret_cast<const uint4*>(ep) : ld_nc_v4(rp + g * 8);
+              const uint32_t r4[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float r0, r1;
-                unpack2<FMT>(rr[e], r0, r1);
+                unpack2<FMT>(r4[e], r0, r1);
                 y[2 * e] += r0, y[2 * e + 1] += r1;
               }
             }
@@ -276,14 +250,107 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
 #pragma unroll
               for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
             }
-            *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+            const uint4 o = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+            if (p.epi_tma)
+              *reinterpret_cast<uint4*>(ep) = o;  // same thread, same address as the residual chunk it just consumed
+            else
+              *reinterpret_cast<uint4*>(op + g * 8) = o;
+          }
+        }
+        if (p.epi_tma) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            int cx, cy;
+            epi_coords(tile, cx, cy);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_out), "r"(c0), "r"(cx), "r"(cy), "r"(smem_u32(etile))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty_bar));
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
+    };
+    uint4 v1[2], v2[2], v3[2], v4[2];  // corner values; loop carried so that skipped loads leave finite data behind
+#pragma unroll
+    for (int j = 0; j < 2; ++j) v1[j] = v2[j] = v3[j] = v4[j] = make_uint4(0, 0, 0, 0);
+    for (int tile = tile0; tile < tile1; ++tile, ++tile_n) {
+      // this thread's two pixels of the tile: table row (pixel inside the image) and batch offset (b*HW)
+      int pp[2];
+      uint32_t base[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const long long gp = tile_pixel(p, tile, (tid >> 3) + 64 * j, HW);
+        const int b = gp >= 0 ? (int)(gp / HW) : 0;
+        pp[j] = gp >= 0 ? (int)(gp - (long long)b * HW) : -1;
+        base[j] = (uint32_t)b * (uint32_t)HW;
+      }
+      // Stage order is HALF-major (all 9 taps of channels 0..63, then of 64..127): the 36 corner reads of a phase then
+      // touch only ~3 image rows x 128 B per pixel (~50 KB), which stays L1 resident; tap-major order alternated between the
+      // two halves and thrashed the ~120 KB L1 (ncu: 44 % hit rate).  Table entries of the next stage are prefetched.
+      int4 ten[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) ten[j] = __ldg(p.table + ((size_t)0 * HW + max(pp[j], 0)));
+      const uint32_t wmask0 = pp[0] >= 0 ? 0xffffffffu : 0u, wmask1 = pp[1] >= 0 ? 0xffffffffu : 0u;
+      const ptrdiff_t rowC = (ptrdiff_t)p.W * C;
+      for (int s = 0; s < nstage_tile; ++s, ++stage) {
+        if (s == 1 && tile > tile0) epilogue(tile - 1, tile_n - 1);
+        if (s == 4 && p.epi_tma && p.res != nullptr && grp < ngrp && lane == 0) {
+          // this tile's residual piece -> the warp's epilogue tile (free once the previous tile's output store has read it)
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          int cx, cy;
+          epi_coords(tile, cx, cy);
+          const uint32_t bar = smem_u32(res_bar + warp);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(etile)),
+                       "l"(&tm_res), "r"(grp * 32), "r"(cx), "r"(cy), "r"(bar)
+                       : "memory");
+        }
+        const int half = s / 9;
+        uint32_t w12[2], w34[2];  // bilinear weights, 16-bit, in the layer's storage format
+        const int coff = half * 64 + kc * 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {  // all 8 corner loads in flight before the first use
+          // Corners with weight exactly 0 are not fetched: the dropped ones (reference edge rules), and 7 of the 36 on a
+          // Cassini / ERP grid -- the centre tap and the two taps on the pixel's own meridian sample at integer coordinates.
+          // Their registers keep an older (finite) value, and 0 * finite == 0.  (The reference multiplies the kept ones by 0;
+          // the only observable difference would be a NaN from an Inf/NaN input.)
+          w12[j] = (uint32_t)ten[j].y & (j ? wmask1 : wmask0), w34[j] = (uint32_t)ten[j].z & (j ? wmask1 : wmask0);
+          const uint16_t* xp = p.x + (ptrdiff_t)(((int)base[j] + ten[j].x) * C + coff);  // may be negative for a dropped top-left corner
+          ldg_if(v1[j], xp, w12[j] & 0xffffu);
+          ldg_if(v2[j], xp + C, w12[j] >> 16);
+          ldg_if(v3[j], xp + rowC, w34[j] & 0xffffu);
+          ldg_if(v4[j], xp + rowC + C, w34[j] >> 16);
+        }
+        if (s + 1 < nstage_tile) {  // prefetch the next stage's table entries (in flight during the blend)
+          const int kn = (s + 1) % 9;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) ten[j] = __ldg(p.table + ((size_t)kn * HW + max(pp[j], 0)));
+        }
+        {
+          const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
+          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+          uint8_t* a_s = smem + (size_t)slot * stage_bytes;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 o;
+            o.x = blend2<FMT>(w12[j], w34[j], v1[j].x, v2[j].x, v3[j].x, v4[j].x);
+            o.y = blend2<FMT>(w12[j], w34[j], v1[j].y, v2[j].y, v3[j].y, v4[j].y);
+            o.z = blend2<FMT>(w12[j], w34[j], v1[j].z, v2[j].z, v3[j].z, v4[j].z);
+            o.w = blend2<FMT>(w12[j], w34[j], v1[j].w, v2[j].w, v3[j].w, v4[j].w);
+            const int pix_l = (tid >> 3) + 64 * j;
+            *reinterpret_cast<uint4*>(a_s + kc * kChunkStrideA + pix_l * 16) = o;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
+        }
+      }
     }
+    if (tile1 > tile0) epilogue(tile1 - 1, tile_n - 1);
+    if (p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == kGatherWarps + 1) {
     // =================================================== weight loader: one bulk copy (TMA, 1-D) per stage, up to kStagesS ahead
     if (lane == 0) {
@@ -308,8 +375,10 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
     const uint32_t a_hi = desc_hi(128), b_hi = desc_hi(128);
     uint32_t stage = 0, tile_n = 0;
     for (int tile = tile0; tile < tile1; ++tile, ++tile_n) {
-      mbar_wait(smem_u32(tempty_bar), (tile_n & 1) ^ 1);  // epilogue of the previous tile has drained the accumulator
+      const uint32_t buf = tile_n & 1;
+      mbar_wait(smem_u32(tempty_bar + buf), ((tile_n >> 1) & 1) ^ 1);  // epilogue of tile - 2 has drained this accumulator
       tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * (uint32_t)p.Co;
       for (int s = 0; s < nstage_tile; ++s, ++stage) {
         const uint32_t slot = stage % kStagesS, phase = (stage / kStagesS) & 1;
         mbar_wait(smem_u32(full_bar + slot), phase);
@@ -319,9 +388,9 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
           const uint32_t b0 = desc_lo(smem_u32(smem + (size_t)slot * stage_bytes + kABytes), (uint32_t)p.Co * 16);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            umma(tmem_base, a0 + ((ks * 2 * kChunkStrideA) >> 4), a_hi, b0 + ((uint32_t)(ks * 2 * p.Co * 16) >> 4), b_hi, idesc, (s | ks) ? 1u : 0u);
+            umma(tacc, a0 + ((ks * 2 * kChunkStrideA) >> 4), a_hi, b0 + ((uint32_t)(ks * 2 * p.Co * 16) >> 4), b_hi, idesc, (s | ks) ? 1u : 0u);
           umma_commit(smem_u32(empty_bar + slot));
-          if (s == nstage_tile - 1) umma_commit(smem_u32(tfull_bar));
+          if (s == nstage_tile - 1) umma_commit(smem_u32(tfull_bar + buf));
         }
         __syncwarp();
       }
@@ -332,34 +401,31 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
   if (warp == kGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
-// gather table: for every (tap, pixel) the four corner pixel indices and bilinear weights, with the reference's rules
-// (kernel.cu:246 tap guard, :97-107 per-corner guards, :109 weights).  Depends only on the sampling grid.
-__global__ void sphere_table_kernel(const float* __restrict__ pos, int4* __restrict__ table, int H, int W, int KK) {
+// gather table: for every (tap, pixel) the top-left corner's pixel index (the other three are +1, +W, +W+1) and the four
+// bilinear weights rounded to the layer's 16-bit storage format, with the reference's rules folded in (kernel.cu:246 tap
+// guard, :97-107 per-corner guards -> weight 0, :109 weights).  A corner of weight 0 is never fetched, so its index may
+// point outside the image.  16 bytes per entry; depends only on the sampling grid and the format.
+__global__ void sphere_table_kernel(const float* __restrict__ pos, int4* __restrict__ table, int H, int W, int KK, int fmt) {
   const int HW = H * W;
   const long long n = (long long)KK * HW;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(e / HW), pp = (int)(e - (long long)k * HW);
     const float h_im = pos[(size_t)(2 * k) * HW + pp], w_im = pos[(size_t)(2 * k + 1) * HW + pp];
-    int4 ix = make_int4(-1, -1, -1, -1);
+    int idx = 0;
     float4 wt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
       const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
       const int h_high = h_low + 1, w_high = w_low + 1;
       const float lh = h_im - h_low, lw = w_im - w_low, hh = 1 - lh, hw = 1 - lw;
-      wt = make_float4(hh * hw, hh * lw, lh * hw, lh * lw);
-      if (h_low >= 0 && w_low >= 0) ix.x = h_low * W + w_low;
-      if (h_low >= 0 && w_high <= W - 1) ix.y = h_low * W + w_high;
-      if (h_high <= H - 1 && w_low >= 0) ix.z = h_high * W + w_low;
-      if (h_high <= H - 1 && w_high <= W - 1) ix.w = h_high * W + w_high;
+      idx = h_low * W + w_low;
+      if (h_low >= 0 && w_low >= 0) wt.x = hh * hw;
+      if (h_low >= 0 && w_high <= W - 1) wt.y = hh * lw;
+      if (h_high <= H - 1 && w_low >= 0) wt.z = lh * hw;
+      if (h_high <= H - 1 && w_high <= W - 1) wt.w = lh * lw;
     }
-    // dropped corners: weight 0 and a valid dummy index, so the gather needs no predication (0 * x == 0 for finite x;
-    // the reference never reads those pixels -- the only observable difference would be an Inf/NaN at pixel 0)
-    if (ix.x < 0) ix.x = 0, wt.x = 0.f;
-    if (ix.y < 0) ix.y = 0, wt.y = 0.f;
-    if (ix.z < 0) ix.z = 0, wt.z = 0.f;
-    if (ix.w < 0) ix.w = 0, wt.w = 0.f;
-    table[2 * e] = ix;
-    table[2 * e + 1] = *reinterpret_cast<int4*>(&wt);
+    const uint32_t w12 = (uint32_t)float_to_h16_bits(wt.x, fmt) | ((uint32_t)float_to_h16_bits(wt.y, fmt) << 16);
+    const uint32_t w34 = (uint32_t)float_to_h16_bits(wt.z, fmt) | ((uint32_t)float_to_h16_bits(wt.w, fmt) << 16);
+    table[e] = make_int4(idx, (int)w12, (int)w34, 0);
   }
 }
 
@@ -380,6 +446,29 @@ __global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __res
   }
 }
 
+int make_epi_tmap(CUtensorMap* tm, const void* ptr, int fmt, int Co, int W, long long rows) {
+  static decltype(&cuTensorMapEncodeTiled) encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      set_error("sphere_conv_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return MODE_ECUDA;
+    }
+    encode = reinterpret_cast<decltype(&cuTensorMapEncodeTiled)>(fn);
+  }
+  const cuuint64_t gdim[3] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)rows};
+  const cuuint64_t gstr[2] = {(cuuint64_t)Co * 2, (cuuint64_t)W * Co * 2};
+  const cuuint32_t box[3] = {32, 16, 2}, estr[3] = {1, 1, 1};
+  const CUresult r = encode(tm, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("sphere_conv_tc: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return MODE_ECUDA;
+  }
+  return MODE_OK;
+}
+
 }  // namespace
 
 extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_h16* w_packed, int C, int Co, int fmt, void* stream) {
@@ -391,12 +480,13 @@ extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_h16* w_packed,
   return MODE_OK;
 }
 
-extern "C" size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw) { return (size_t)32 * Kh * Kw * H * W; }
+extern "C" size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw) { return (size_t)16 * Kh * Kw * H * W; }
 
-extern "C" int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, void* stream) {
+extern "C" int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, int fmt, void* stream) {
   MODE_CHECK_ARG(pos && table && H > 0 && W > 0 && Kh > 0 && Kw > 0, "sphere_conv_build_table: bad arguments");
+  MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "sphere_conv_build_table: fmt must be 0 (bf16) or 1 (fp16)");
   const long long n = (long long)Kh * Kw * H * W;
-  sphere_table_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, (int4*)table, H, W, Kh * Kw);
+  sphere_table_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, (int4*)table, H, W, Kh * Kw, fmt);
   MODE_CHECK_LAUNCH("sphere_conv_build_table");
   return MODE_OK;
 }
@@ -412,7 +502,7 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
   p.x = x, p.table = (const int4*)table, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.out = out;
   p.B = B, p.C = C, p.H = H, p.W = W, p.Co = Co, p.relu = relu;
   p.npix = (long long)B * H * W;
-  MODE_CHECK_ARG(p.npix * C < 4294967295LL, "sphere_conv_tc: activation tensor too large for 32-bit offsets");
+  MODE_CHECK_ARG((p.npix + W + 1) * C < 2147483647LL, "sphere_conv_tc: activation tensor too large for 32-bit offsets");
   if (W % 16 == 0 && H % 8 == 0) {
     p.tw = 16, p.th = 8, p.tiles_x = W / 16, p.tiles_y = H / 8;
     p.ntiles = B * p.tiles_x * p.tiles_y;
@@ -420,23 +510,42 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
     p.tw = 0, p.th = 0, p.tiles_x = p.tiles_y = 0;
     p.ntiles = (int)((p.npix + 127) / 128);
   }
-  const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + (2 * kStagesS + 2) * 8 + 16;
+  const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + 1024 + kGatherWarps * 2048 + (2 * kStagesS + 4 + kGatherWarps) * 8 + 16;
   static thread_local size_t attr = 0;
   if (smem > attr) {
-    MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
-    MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
     // one CTA per SM: leave the rest of the 228 KB to L1 -- the 9 taps x 4 corners of a tile re-read the same ~45 KB
     // of input, which must stay L1 resident (with a maximal carve-out the kernel was L2-bandwidth bound: 3.6 GB/launch)
     const int carve = (int)((smem + 8 * 1024) * 100 / (228 * 1024)) + 1;
-    cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtBF16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    cudaFuncSetAttribute(sphere_conv_tc_kernel<kFmtFP16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    const void* kernels[4] = {(const void*)sphere_conv_tc_kernel<kFmtBF16, 0>, (const void*)sphere_conv_tc_kernel<kFmtFP16, 0>,
+                              (const void*)sphere_conv_tc_kernel<kFmtBF16, 128>, (const void*)sphere_conv_tc_kernel<kFmtFP16, 128>};
+    for (const void* k : kernels) {
+      MODE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_tc");
+      cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
     attr = smem;
   }
+  // epilogue tiles through TMA: (Co, W, B*H) view of the NHWC output / residual, box 32 ch x 16 x 2, 64-byte swizzle
+  CUtensorMap tm_out, tm_res;
+  memset(&tm_out, 0, sizeof(tm_out));
+  memset(&tm_res, 0, sizeof(tm_res));
+  p.epi_tma = (p.tw == 16 && (Co == 64 || Co == 128) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) ? 1 : 0;
+  if (p.epi_tma) {
+    int rc = make_epi_tmap(&tm_out, out, fmt, Co, W, (long long)B * H);
+    if (rc == MODE_OK && residual) rc = make_epi_tmap(&tm_res, residual, fmt, Co, W, (long long)B * H);
+    if (rc != MODE_OK) return rc;
+  }
   const int grid = std::min(p.ntiles, kNumSMs);
-  if (fmt == kFmtBF16)
-    sphere_conv_tc_kernel<kFmtBF16><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
-  else
-    sphere_conv_tc_kernel<kFmtFP16><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p);
+  if (C == 128) {
+    if (fmt == kFmtBF16)
+      sphere_conv_tc_kernel<kFmtBF16, 128><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+    else
+      sphere_conv_tc_kernel<kFmtFP16, 128><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+  } else {
+    if (fmt == kFmtBF16)
+      sphere_conv_tc_kernel<kFmtBF16, 0><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+    else
+      sphere_conv_tc_kernel<kFmtFP16, 0><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+  }
   MODE_CHECK_LAUNCH("sphere_conv_tc");
   return MODE_OK;
 }

@@ -163,16 +163,17 @@ def sphere_conv_pack_weights(weight: torch.Tensor, dtype=torch.bfloat16) -> torc
 _TABLES = {}
 
 
-def sphere_gather_table(pos: torch.Tensor) -> torch.Tensor:
-  """Pre-digested sampling grid for the tensor-core kernel (cached per grid tensor): see mode_sphere_conv_build_table."""
+def sphere_gather_table(pos: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+  """Pre-digested sampling grid for the tensor-core kernel (cached per grid tensor and 16-bit format): see
+  mode_sphere_conv_build_table."""
   pos = _chk(pos, torch.float32, 'sphere_gather_table')
-  key = (pos.data_ptr(), tuple(pos.shape), pos._version)
+  key = (pos.data_ptr(), tuple(pos.shape), pos._version, dtype)
   if key not in _TABLES:
     H, W = pos.shape[-2:]
     if pos.numel() != 18 * H * W:
       raise RuntimeError(f'invalid spatial size of position, expected 18x{H}x{W}, got {tuple(pos.shape)}')
     table = torch.empty(_lib.load().mode_sphere_conv_table_bytes(H, W, 3, 3), dtype=torch.uint8, device=pos.device)
-    _lib.call('mode_sphere_conv_build_table', _p(pos), _p(table), H, W, 3, 3, _stream())
+    _lib.call('mode_sphere_conv_build_table', _p(pos), _p(table), H, W, 3, 3, _fmt(dtype), _stream())
     _TABLES[key] = (table, pos)  # keep `pos` alive so the data_ptr key stays unique
   return _TABLES[key][0]
 
@@ -196,7 +197,7 @@ def sphere_conv_bf16(x: torch.Tensor, pos: torch.Tensor, w_packed: torch.Tensor,
   out = torch.empty((B, H, W, cout), dtype=x.dtype, device=x.device)
   if residual is not None and residual.shape != out.shape:
     raise RuntimeError('sphere_conv_bf16: residual shape mismatch')
-  _lib.call('mode_sphere_conv_tc', _p(x), _p(sphere_gather_table(pos)), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
+  _lib.call('mode_sphere_conv_tc', _p(x), _p(sphere_gather_table(pos, x.dtype)), _p(w_packed), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
             _p(_opt(residual, x.dtype, 'residual')), _p(out), B, Cc, H, W, cout, int(relu), fmt, _stream())
   return out
 
