@@ -26,6 +26,7 @@
 // plane directly in the UMMA layout; out-of-bounds box elements are zero-filled by the TMA unit = the conv padding.
 // Pipelines: smem ring full/empty (producer <-> MMA), TMEM set full/empty (MMA <-> epilogue).
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 using namespace mode;
@@ -39,7 +40,7 @@ namespace {
 template <int MODE>
 constexpr int epi_warps() { return MODE == 2 ? 16 : 4; }
 template <int MODE>
-constexpr int num_threads() { return (epi_warps<MODE>() + 2) * 32; }
+constexpr int num_threads() { return (epi_warps<MODE>() + 2 + (MODE == 2 ? 1 : 0)) * 32; }  // + MMA warp, TMA producer, (transposed conv) residual loader
 constexpr int kMaxSlots = 8;
 constexpr int kMaxSets = 32;  // TMEM accumulator blocks (512 columns / NT) or sets (transposed conv)
 constexpr int kWHalf = 32;  // the packed weights are organised in 32-input-channel halves
@@ -261,7 +262,7 @@ __device__ __forceinline__ int out_plane(int pl, int kd) {
 __host__ __device__ inline int wblock_of_kd(int mode, int kd) { return mode == 0 ? 2 - kd : mode == 2 ? kd : (kd == 2 ? 0 : (kd == 0 ? 1 : 2)); }
 
 template <int MODE, int NT, int FMT, int SC>
-__global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_res) {
   using G = Geo<MODE>;
   constexpr int kEpiWarps = epi_warps<MODE>();
   constexpr int kThreads = num_threads<MODE>();
@@ -293,17 +294,28 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
   uint8_t* slots_s = smem + ((w_bytes + 1023) & ~1023u);  // swizzled boxes: 1024-byte aligned
-  // transposed conv: per-warp 2 KB + 2 KB staging tiles (residual in / output out) used to turn the row-per-thread epilogue
-  // accesses (64 B per thread at a 128 B stride = 32 L1 wavefronts per instruction) into lane-contiguous ones
+  // transposed conv: staging tiles [parity class 4][buffer 2][quadrant 4] x 2 KB (32 voxels x 32 channels, 64-byte swizzle),
+  // one per epilogue warp and buffer.  The residual of a plane arrives there by TMA -- one stride-2 box per class over the
+  // output-shaped tensor, issued by a dedicated loader warp up to two planes ahead, so its HBM latency and the issue cost
+  // are off the epilogue's per-plane critical path -- the output piece is staged in the same tile and leaves through
+  // lane-contiguous 16-byte stores (row-per-thread global accesses, 64 B per thread at a 128 B stride, cost 32 L1
+  // wavefronts per instruction).
   uint8_t* epi_s = slots_s + (size_t)p.nslots * kSlotBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_s + (MODE == 2 ? kEpiWarps * 4096 : 0));
   uint64_t* full_bar = bars;                               // [nslots] producers -> MMA
   uint64_t* empty_bar = bars + kMaxSlots;                  // [nslots] MMA (commit) -> producers
   uint64_t* tfull_bar = bars + 2 * kMaxSlots;              // [R]      MMA (commit) -> epilogue
   uint64_t* tempty_bar = bars + 2 * kMaxSlots + kMaxSets;  // [R]      epilogue -> MMA
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxSets);
+  uint64_t* rfull_bar = bars + 2 * kMaxSlots + 2 * kMaxSets;  // [class 4][buffer 2] residual loader -> epilogue (transposed conv)
+  uint64_t* rempty_bar = rfull_bar + 8;                       // [class 4][buffer 2] epilogue (4 warps) -> residual loader
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxSets + (MODE == 2 ? 2 * kEpiWarps : 0));
 
   if (threadIdx.x == 0) {
+    if (MODE == 2)
+      for (int i = 0; i < 8; ++i) {
+        mbar_init(smem_u32(rfull_bar + i), 1);
+        mbar_init(smem_u32(rempty_bar + i), 4);
+      }
     for (int i = 0; i < p.nslots; ++i) {
       mbar_init(smem_u32(full_bar + i), 1);
       mbar_init(smem_u32(empty_bar + i), 1);
@@ -343,7 +355,32 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= kEpiWarps + 1) {
+  if (MODE == 2 && warp == kEpiWarps + 2) {
+    // =========================================================== RESIDUAL LOADER (transposed conv, one lane)
+    if (lane == 0 && p.res != nullptr) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_res)) : "memory");
+      uint32_t n = 0;  // output planes in the order the epilogue drains them
+      for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
+        const Item it = decode_item(p, nb_of_cta * per_nb + li);
+        int p0, p1, o0, o1;
+        chunk_ranges<MODE>(p, it.ch, p0, p1, o0, o1);
+        for (int od = o0; od < o1; ++od, ++n) {
+          const uint32_t buf = n & 1, use = n >> 1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            mbar_wait(smem_u32(rempty_bar + c * 2 + buf), (use & 1) ^ 1);
+            const uint32_t bar = smem_u32(rfull_bar + c * 2 + buf);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8192) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                             smem_u32(epi_s + (size_t)(c * 2 + buf) * 8192)),
+                         "l"(reinterpret_cast<uint64_t>(&tmap_res)), "r"(it.nb * NT), "r"(2 * (it.tw * 8) + (c & 1)), "r"(2 * (it.th * 16) + (c >> 1)), "r"(it.b * p.Do + od),
+                         "r"(bar)
+                         : "memory");
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps + 1) {
     // =========================================================== TMA PRODUCER (one lane)
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
@@ -601,6 +638,8 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
     const int hl = row >> 3, wl = row & 7;
     uint32_t job_base = 0, use_mask = 0;
     long long dbg_tfull = 0;
+    const bool res_tma = MODE == 2 && p.res != nullptr;
+    uint32_t nplane = 0;  // transposed conv: output planes drained so far (staging buffer = nplane & 1)
     for (int li = lane_cta; li < per_nb; li += ctas_per_nb) {
       const Item it = decode_item(p, nb_of_cta * per_nb + li);
       int p0, p1, o0, o1;
@@ -630,8 +669,8 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
         uint4 rpre[NT / 8];
         const float rpre_f32 = (ok && p.res_f32) ? __ldg(p.res_f32 + vox * p.CoReal) : 0.f;
         // lane-contiguous view of this warp's 32 rows x 64 B: instruction k, lane t <-> row 8k + (t >> 2), 16-byte chunk t & 3
-        uint8_t* tile_res = epi_s + (size_t)warp * 4096;
-        uint8_t* tile_out = tile_res + 2048;
+        uint8_t* tile_res = epi_s + (size_t)(((cls * 2 + (nplane & 1)) * 4 + (warp & 3)) * 2048);
+        uint8_t* tile_out = tile_res;  // a thread overwrites exactly the chunks it has just read
         size_t vox_c[4];
         bool ok_c[4];
         if (MODE == 2 && NT == 32) {
@@ -641,17 +680,8 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
             ok_c[k] = ih < p.Hi && iw < p.Wi;
             vox_c[k] = (((size_t)it.b * p.Do + od) * p.Ho + (2 * ih + (cls >> 1))) * p.Wo + (2 * iw + (cls & 1));
           }
-          __syncwarp();  // previous job's reads of the staging tiles are done
-          if (p.res) {
-            uint4 rc[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rc[k] = ok_c[k] ? ld_nc_v4(p.res + vox_c[k] * p.Co + n0 + (lane & 3) * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int r = 8 * k + (lane >> 2);
-              *reinterpret_cast<uint4*>(tile_res + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4)) = rc[k];
-            }
-            __syncwarp();
+          if (res_tma) {
+            mbar_wait(smem_u32(rfull_bar + cls * 2 + (nplane & 1)), (nplane >> 1) & 1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) rpre[q] = *reinterpret_cast<const uint4*>(tile_res + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4));
           }
@@ -728,12 +758,21 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
         }
         if (MODE == 2 && NT == 32 && p.out_f32 == nullptr) {
           __syncwarp();
+          uint4 o[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int r = 8 * k + (lane >> 2);
-            const uint4 o = *reinterpret_cast<const uint4*>(tile_out + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
-            if (ok_c[k]) *reinterpret_cast<uint4*>(p.out + vox_c[k] * p.Co + n0 + (lane & 3) * 8) = o;
+            o[k] = *reinterpret_cast<const uint4*>(tile_out + r * 64 + (((lane & 3) ^ ((r >> 1) & 3)) << 4));
           }
+          if (res_tma) {  // the tile is free again (before the global stores, so that the fence does not wait on them)
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(rempty_bar + cls * 2 + (nplane & 1)));
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (ok_c[k]) *reinterpret_cast<uint4*>(p.out + vox_c[k] * p.Co + n0 + (lane & 3) * 8) = o[k];
+          ++nplane;
         }
         tmem_st_wait();
         tc_fence_before();
@@ -832,24 +871,47 @@ int make_tmap(CUtensorMap* tm, const void* x, int fmt, int C, int Wi, int Hi, lo
   return MODE_OK;
 }
 
+int make_tmap_res(CUtensorMap* tm, const void* ptr, int fmt, int Co, int Wo, int Ho, long long planes) {
+  static decltype(&cuTensorMapEncodeTiled) encode = nullptr;
+  if (!encode) {
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      set_error("conv3d_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return MODE_ECUDA;
+    }
+    encode = reinterpret_cast<decltype(&cuTensorMapEncodeTiled)>(fn);
+  }
+  const cuuint64_t gdim[4] = {(cuuint64_t)Co, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)planes};
+  const cuuint64_t gstr[3] = {(cuuint64_t)Co * 2, (cuuint64_t)Wo * Co * 2, (cuuint64_t)Ho * Wo * Co * 2};
+  const cuuint32_t box[4] = {32, 16, 32, 1}, estr[4] = {1, 2, 2, 1};  // 8 columns x 16 rows at element stride 2 = one parity class of a tile
+  const CUresult r = encode(tm, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("conv3d_tc: cuTensorMapEncodeTiled (residual) failed (CUresult %d)", (int)r);
+    return MODE_ECUDA;
+  }
+  return MODE_OK;
+}
+
 template <int MODE, int NT, int FMT, int SC>
-int launch_tc3(const TcParams& p, const CUtensorMap& tm, int grid, size_t smem, cudaStream_t s) {
+int launch_tc3(const TcParams& p, const CUtensorMap& tm, const CUtensorMap& tmr, int grid, size_t smem, cudaStream_t s) {
   static thread_local size_t attr = 0;
   if (smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
     attr = smem;
   }
-  conv3d_tc_kernel<MODE, NT, FMT, SC><<<grid, num_threads<MODE>(), smem, s>>>(p, tm);
+  conv3d_tc_kernel<MODE, NT, FMT, SC><<<grid, num_threads<MODE>(), smem, s>>>(p, tm, tmr);
   MODE_CHECK_LAUNCH("conv3d_tc");
   return MODE_OK;
 }
 template <int MODE, int NT, int FMT>
-int launch_tc2(const TcParams& p, const CUtensorMap& tm, int sc, int grid, size_t smem, cudaStream_t s) {
-  return sc == 32 ? launch_tc3<MODE, NT, FMT, 32>(p, tm, grid, smem, s) : launch_tc3<MODE, NT, FMT, 64>(p, tm, grid, smem, s);
+int launch_tc2(const TcParams& p, const CUtensorMap& tm, const CUtensorMap& tmr, int sc, int grid, size_t smem, cudaStream_t s) {
+  return sc == 32 ? launch_tc3<MODE, NT, FMT, 32>(p, tm, tmr, grid, smem, s) : launch_tc3<MODE, NT, FMT, 64>(p, tm, tmr, grid, smem, s);
 }
 template <int MODE, int NT>
-int launch_tc(const TcParams& p, const CUtensorMap& tm, int sc, int fmt, int grid, size_t smem, cudaStream_t s) {
-  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, tm, sc, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, tm, sc, grid, smem, s);
+int launch_tc(const TcParams& p, const CUtensorMap& tm, const CUtensorMap& tmr, int sc, int fmt, int grid, size_t smem, cudaStream_t s) {
+  return fmt == kFmtBF16 ? launch_tc2<MODE, NT, kFmtBF16>(p, tm, tmr, sc, grid, smem, s) : launch_tc2<MODE, NT, kFmtFP16>(p, tm, tmr, sc, grid, smem, s);
 }
 
 }  // namespace
@@ -911,7 +973,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   const size_t w_bytes = ((size_t)(Ci / kWHalf) * 27 * 4 * NT * 16 + 1023) & ~(size_t)1023;
   const size_t nvox = (mode == 0) ? Geo<0>::NVOX : Geo<1>::NVOX, nbox = (mode == 1) ? 4 : 1;
   const size_t slot_bytes = nbox * (((nvox * SC * 2) + 1023) & ~(size_t)1023);
-  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets) * 8 + 16 + 128 + 1024 + (mode == 2 ? 16 * 4096 : 0);  // barriers, smem base alignment, epilogue staging
+  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets + 32) * 8 + 16 + 128 + 1024 + (mode == 2 ? 16 * 4096 : 0);  // barriers, smem base alignment, epilogue staging
   const size_t budget = 227 * 1024;
   // Two co-resident CTAs per SM when they fit (stride-1 / stride-2 layers with <= 55 KB of weights): the MMA-issuing warp is
   // bound by its own instruction latency (~1700 cycles of waits + bookkeeping + issue per 18-MMA stage against ~1000 cycles of
@@ -960,13 +1022,21 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
     const int rc = make_tmap(&tm, x, fmt, Ci, Wi, Hi, (long long)B * Di, mode, SC);
     if (rc != MODE_OK) return rc;
   }
-  if (NT == 32) {
-    if (mode == 0) return launch_tc<0, 32>(p, tm, SC, fmt, grid, smem, s);
-    if (mode == 1) return launch_tc<1, 32>(p, tm, SC, fmt, grid, smem, s);
-    return launch_tc<2, 32>(p, tm, SC, fmt, grid, smem, s);
+  // transposed conv with a residual: stride-2 box (one parity class of a 16 x 8 tile -> 128 output voxels x 32 channels)
+  // over the output-shaped residual tensor, (Co, Wo, Ho, B*Do)
+  CUtensorMap tmr;
+  memset(&tmr, 0, sizeof(tmr));
+  if (mode == 2 && residual != nullptr) {
+    const int rc = make_tmap_res(&tmr, residual, fmt, Co, p.Wo, p.Ho, (long long)B * p.Do);
+    if (rc != MODE_OK) return rc;
   }
-  if (mode == 0) return launch_tc<0, 16>(p, tm, SC, fmt, grid, smem, s);
-  if (mode == 1) return launch_tc<1, 16>(p, tm, SC, fmt, grid, smem, s);
+  if (NT == 32) {
+    if (mode == 0) return launch_tc<0, 32>(p, tm, tmr, SC, fmt, grid, smem, s);
+    if (mode == 1) return launch_tc<1, 32>(p, tm, tmr, SC, fmt, grid, smem, s);
+    return launch_tc<2, 32>(p, tm, tmr, SC, fmt, grid, smem, s);
+  }
+  if (mode == 0) return launch_tc<0, 16>(p, tm, tmr, SC, fmt, grid, smem, s);
+  if (mode == 1) return launch_tc<1, 16>(p, tm, tmr, SC, fmt, grid, smem, s);
   set_error("conv3d_tc: unsupported configuration");
   return MODE_ENOSUP;
 }

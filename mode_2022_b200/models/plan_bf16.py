@@ -21,8 +21,16 @@ class _FoldedConv2d:
     scale, shift = bn_affine(bn)
     w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1)
     self.w = w.to(dtype).contiguous(memory_format=torch.channels_last)
+    self.shift = shift.float()
     self.b = shift.to(dtype)
     self.stride, self.padding, self.dilation = conv.stride, conv.padding, conv.dilation
+
+  def move_bias_into(self, other: '_FoldedConv2d'):
+    """This conv's output is only ever added to `other`'s pre-activation (a BasicBlock's downsample branch): give the
+    BN shift to `other`, so that this conv runs bias-free instead of paying a separate elementwise bias pass."""
+    other.shift = other.shift + self.shift
+    other.b = other.shift.to(other.b.dtype)
+    self.shift, self.b = None, None
 
   def __call__(self, x, relu, residual=None):
     """conv + folded-BN bias [+ residual] [+ ReLU]; uses cuDNN's fused conv-bias-(add)-ReLU when available."""
@@ -73,7 +81,10 @@ class Bf16Plan(_PlanBase):
       blocks = []
       for blk in layer:
         ds = _FoldedConv2d(blk.downsample[0], blk.downsample[1], dtype) if blk.downsample is not None else None
-        blocks.append((_FoldedConv2d(blk.conv1[0][0], blk.conv1[0][1], dtype), _FoldedConv2d(blk.conv2[0], blk.conv2[1], dtype), ds))
+        c2 = _FoldedConv2d(blk.conv2[0], blk.conv2[1], dtype)
+        if ds is not None:
+          ds.move_bias_into(c2)
+        blocks.append((_FoldedConv2d(blk.conv1[0][0], blk.conv1[0][1], dtype), c2, ds))
       self.regular.append(blocks)
     lc = fe.lastconv
     self.last = [_FoldedConv2d(lc[0][0], lc[0][1], dtype), _FoldedConv2d(lc[2][0], lc[2][1], dtype), _FoldedConv2d(lc[4][0], lc[4][1], dtype)]

@@ -51,3 +51,6 @@ for i in (0, 1, 2, 3, 4, 5, 6, 7, 144, 145, 146, 147):
 for c in range(4):
   ts = st[c, :60].tolist()
   print('cta', c, 'stage deltas (cycles):', ' '.join(str(int(b - a)) for a, b in zip(ts[:-1], ts[1:])))
+
+for c in range(4):
+  print('cta', c, 'raw seg:', ' '.join(str(int(v)) for v in st[c, :12].tolist()))
