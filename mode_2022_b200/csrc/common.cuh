@@ -88,6 +88,28 @@ __device__ __forceinline__ float h16_bits_to_float(uint16_t b, int fmt) {
   return __half2float(*reinterpret_cast<const __half*>(&b));
 }
 
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): two lanes per instruction
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\tfma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// max(x, 0) on a packed 16-bit pair (ReLU after rounding == rounding after ReLU: rounding is monotonic and keeps 0)
+template <int FMT>
+__device__ __forceinline__ uint32_t relu2(uint32_t v) {
+  if (FMT == kFmtBF16) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&v), __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 // streaming 128-bit accesses: data touched once should not pollute L1
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
   uint4 r;

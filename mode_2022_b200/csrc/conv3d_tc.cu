@@ -309,6 +309,14 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
   uint64_t* rfull_bar = bars + 2 * kMaxSlots + 2 * kMaxSets;  // [class 4][buffer 2] residual loader -> epilogue (transposed conv)
   uint64_t* rempty_bar = rfull_bar + 8;                       // [class 4][buffer 2] epilogue (4 warps) -> residual loader
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 2 * kMaxSets + (MODE == 2 ? 2 * kEpiWarps : 0));
+  // BN affine of all output channels, interleaved per 4 channels as {scale x4, shift x4} (1 / 0 where the caller passed NULL):
+  // the epilogue applies it unconditionally with packed FFMA2 fed by broadcast LDS.128
+  float4* ss_s = reinterpret_cast<float4*>(tmem_ptr_s + 4);
+  for (int c = threadIdx.x; c < p.Co; c += kThreads) {
+    float* e = reinterpret_cast<float*>(ss_s + 2 * (c >> 2)) + (c & 3);
+    e[0] = (p.scale && c < p.CoReal) ? p.scale[c] : 1.f;
+    e[4] = (p.shift && c < p.CoReal) ? p.shift[c] : 0.f;
+  }
 
   if (threadIdx.x == 0) {
     if (MODE == 2)
@@ -721,16 +729,10 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
               for (int q = 0; q < NT / 8; ++q) {
                 float y[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[q * 8 + j]);
-                if (p.scale) {
-                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q * 8));
-                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + q * 8) + 1);
-                  y[0] *= s0.x, y[1] *= s0.y, y[2] *= s0.z, y[3] *= s0.w, y[4] *= s1.x, y[5] *= s1.y, y[6] *= s1.z, y[7] *= s1.w;
-                }
-                if (p.shift) {
-                  const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q * 8));
-                  const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.shift + n0 + q * 8) + 1);
-                  y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
+                for (int h = 0; h < 2; ++h) {  // y = acc * scale + shift (+ residual), two channels per instruction
+                  const float4 sc = ss_s[2 * ((n0 >> 2) + q * 2 + h)], sh = ss_s[2 * ((n0 >> 2) + q * 2 + h) + 1];
+                  ffma2(y[4 * h], y[4 * h + 1], __uint_as_float(v[q * 8 + 4 * h]), __uint_as_float(v[q * 8 + 4 * h + 1]), sc.x, sc.y, sh.x, sh.y);
+                  ffma2(y[4 * h + 2], y[4 * h + 3], __uint_as_float(v[q * 8 + 4 * h + 2]), __uint_as_float(v[q * 8 + 4 * h + 3]), sc.z, sc.w, sh.z, sh.w);
                 }
                 if (p.res) {
                   const uint4 r = rpre[q];
@@ -739,15 +741,12 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
                   for (int j = 0; j < 4; ++j) {
                     float r0, r1;
                     unpack2<FMT>(rr[j], r0, r1);
-                    y[2 * j] += r0, y[2 * j + 1] += r1;
+                    fadd2(y[2 * j], y[2 * j + 1], y[2 * j], y[2 * j + 1], r0, r1);
                   }
-                }
-                if (p.relu) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
                 uint4 o;
                 o.x = pack2<FMT>(y[0], y[1]), o.y = pack2<FMT>(y[2], y[3]), o.z = pack2<FMT>(y[4], y[5]), o.w = pack2<FMT>(y[6], y[7]);
+                if (p.relu) o.x = relu2<FMT>(o.x), o.y = relu2<FMT>(o.y), o.z = relu2<FMT>(o.z), o.w = relu2<FMT>(o.w);
                 if (MODE == 2 && NT == 32)
                   *reinterpret_cast<uint4*>(tile_out + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = o;  // staged, stored below
                 else
@@ -973,7 +972,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   const size_t w_bytes = ((size_t)(Ci / kWHalf) * 27 * 4 * NT * 16 + 1023) & ~(size_t)1023;
   const size_t nvox = (mode == 0) ? Geo<0>::NVOX : Geo<1>::NVOX, nbox = (mode == 1) ? 4 : 1;
   const size_t slot_bytes = nbox * (((nvox * SC * 2) + 1023) & ~(size_t)1023);
-  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets + 32) * 8 + 16 + 128 + 1024 + (mode == 2 ? 16 * 4096 : 0);  // barriers, smem base alignment, epilogue staging
+  const size_t misc = (2 * kMaxSlots + 2 * kMaxSets + 32) * 8 + 16 + 128 + 1024 + 2 * 64 * 4 + (mode == 2 ? 16 * 4096 : 0);  // barriers, smem base alignment, epilogue staging
   const size_t budget = 227 * 1024;
   // Two co-resident CTAs per SM when they fit (stride-1 / stride-2 layers with <= 55 KB of weights): the MMA-issuing warp is
   // bound by its own instruction latency (~1700 cycles of waits + bookkeeping + issue per 18-MMA stage against ~1000 cycles of
