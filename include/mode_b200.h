@@ -47,6 +47,14 @@ unsigned long long mode_b200_launch_count(void);
 int mode_cost_volume_f32(const float* ref, const float* tgt, float* cost, int B, int C, int H, int W, int D4, void* stream);
 int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mode_h16* cost, int B, int C, int H, int W, int D4, void* stream);
 
+/* ---- a1. stem convolution of the feature extractor (tcgen05) ------------------------------------
+ * replaces sphere_feature_extraction.firstconv[0] = convbn(3, 32, 7, 2, 3, 1) + ReLU (models/submodule.py:155, 15-17, called
+ * from models/mode_disparity.py:99-100): fp32 NCHW images in -- x0 (B0,3,H,W) and optionally x1 (B1,3,H,W), i.e. the
+ * left and right batches without a concatenation pass -- NHWC 16-bit activation (B0+B1, Ho, Wo, 32) out, Ho = (H-1)/2+1.
+ * w (32,3,7,7) fp32; y = conv*scale[co] + shift[co] (ReLU if relu); scale/shift may be NULL.  W <= 2048. */
+int mode_stem_conv_tc(const float* x0, const float* x1, const float* w, const float* scale, const float* shift, mode_h16* out, int B0, int B1, int H, int W,
+                      int relu, int fmt, void* stream);
+
 /* ---- a6/a7. trilinear upsample + softmax + soft-argmin (+ confidence) --------------------------
  * replaces models/mode_disparity.py:143-152 (+131-141 for the training heads), :157-183 and
  * models/submodule.py:50-57.  cost: (B, D4, H4, W4) fp32 -> pred (B, H, W) [, conf (B, H, W) or NULL].

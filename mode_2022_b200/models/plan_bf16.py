@@ -75,6 +75,11 @@ class Bf16Plan(_PlanBase):
     if model.conv_type != 'Sphere':
       raise NotImplementedError("precision='bf16' supports conv='Sphere' (the MODE configuration); use precision='fp32' for conv='Regular'")
     fc = fe.firstconv
+    c0 = fc[0][0]
+    # firstconv[0] (3 -> 32, 7x7, stride 2): own tensor-core kernel reading the fp32 NCHW images directly (ops.stem_conv)
+    self.stem = None
+    if (c0.in_channels, c0.out_channels, c0.kernel_size, c0.stride, c0.padding, c0.dilation) == (3, 32, (7, 7), (2, 2), (3, 3), (1, 1)):
+      self.stem = (_w(c0), *bn_affine(fc[0][1]))
     self.first = [_FoldedConv2d(fc[0][0], fc[0][1], dtype), _FoldedConv2d(fc[2][0], fc[2][1], dtype), _FoldedConv2d(fc[4][0], fc[4][1], dtype)]
     self.regular = []
     for layer in (fe.layer1, fe.layer2, fe.layer3):
@@ -109,9 +114,17 @@ class Bf16Plan(_PlanBase):
       x = c2(c1(x, True), True, residual=res)  # relu(conv2(relu(conv1(x))) + res), reference submodule.py:108-119
     return x
 
-  def features(self, x):
-    x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
-    for c in self.first:
+  def features(self, left, right=None):
+    """left (B,3,H,W) [+ right (B,3,H,W)] -> (B or 2B, 32, H/4, W/4) features; the two batches are stacked along dim 0."""
+    if self.stem is not None and left.shape[-1] <= 2048:
+      w0, s0, h0 = self.stem
+      x = ops.stem_conv(left.float(), None if right is None else right.float(), w0, s0, h0, True, self.dtype == torch.float16).permute(0, 3, 1, 2)
+      rest = self.first[1:]
+    else:
+      x = left if right is None else torch.cat([left, right], 0)
+      x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
+      rest = self.first
+    for c in rest:
       x = c(x, True)
     x = self._regular_layer(x, self.regular[0])
     raw = self._regular_layer(x, self.regular[1])
@@ -155,7 +168,7 @@ class Bf16Plan(_PlanBase):
 
   def run(self, left, right, return_stages=False):
     B, _, H, W = left.shape
-    feat = self.features(torch.cat([left, right], 0))
+    feat = self.features(left, right)
     cost = self.cost_volume(feat[:B], feat[B:], self.maxdisp // 4)
     cost1, cost2, cost3 = self.regularise(cost)
     pred, conf = ops.disp_regress(cost3[..., 0], self.maxdisp, H, W)

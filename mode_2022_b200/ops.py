@@ -207,6 +207,37 @@ def _(x, pos, w_packed, cout, scale, shift, residual, relu):
   return torch.empty((*x.shape[:3], cout), dtype=x.dtype, device=x.device)
 
 
+@torch.library.custom_op('mode_b200::stem_conv', mutates_args=())
+def stem_conv(x0: torch.Tensor, x1: Optional[torch.Tensor], weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], relu: bool,
+              fp16: bool) -> torch.Tensor:
+  """firstconv[0] of the MODE feature extractor (3 -> 32, 7x7, stride 2, pad 3) + affine + ReLU on tcgen05 tensor cores.
+  x0 (B0,3,H,W) and optional x1 (B1,3,H,W) fp32 NCHW (left / right batches, no concatenation) -> (B0+B1, Ho, Wo, 32) NHWC
+  bf16 (fp16 if `fp16`)."""
+  if x0.dim() != 4 or x0.shape[1] != 3:
+    raise ValueError('stem_conv: expected (B,3,H,W) images')
+  x0 = _chk(x0, torch.float32, 'stem_conv')
+  if x1 is not None:
+    x1 = _chk(x1, torch.float32, 'stem_conv')
+    if x1.shape[1:] != x0.shape[1:]:
+      raise ValueError('stem_conv: x0 / x1 image shapes differ')
+  weight = _chk(weight, torch.float32, 'stem_conv')
+  if tuple(weight.shape) != (32, 3, 7, 7):
+    raise ValueError('stem_conv: weight must be (32,3,7,7)')
+  dtype = torch.float16 if fp16 else torch.bfloat16
+  B0, _, H, W = x0.shape
+  B1 = 0 if x1 is None else x1.shape[0]
+  out = torch.empty((B0 + B1, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 32), dtype=dtype, device=x0.device)
+  _lib.call('mode_stem_conv_tc', _p(x0), _p(x1) if x1 is not None else None, _p(weight), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')),
+            _p(out), B0, B1, H, W, int(relu), _fmt(dtype), _stream())
+  return out
+
+
+@stem_conv.register_fake
+def _(x0, x1, weight, scale, shift, relu, fp16):
+  B = x0.shape[0] + (0 if x1 is None else x1.shape[0])
+  return torch.empty((B, (x0.shape[2] - 1) // 2 + 1, (x0.shape[3] - 1) // 2 + 1, 32), dtype=torch.float16 if fp16 else torch.bfloat16, device=x0.device)
+
+
 # ------------------------------------------------------------------------------------------------
 # a5. conv3d family
 # ------------------------------------------------------------------------------------------------

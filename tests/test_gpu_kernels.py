@@ -290,3 +290,28 @@ def test_sphere_conv_bf16_tensor_core(ops, B, C, Co, h, w, st, dtype):
   plain = ops.sphere_conv_bf16(xq.permute(0, 2, 3, 1).contiguous().cuda(), pos.cuda(), wp, Co, None, None, None, False).float().cpu().permute(0, 3, 1, 2)
   want_plain = O.sphere_conv(xq.float(), pos, wq.float())
   assert ((plain - want_plain).abs() <= rel * want_plain.abs().clamp_min(1.0)).all()
+
+
+# ---------------------------------------------------------------------------- a1 stem conv (3 -> 32, 7x7, stride 2) on tensor cores
+@pytest.mark.parametrize('B0,B1,h,w', [(1, 0, 16, 24), (2, 1, 64, 48), (1, 1, 50, 300), (1, 1, 256, 512), (1, 0, 33, 700)])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_stem_conv_tensor_core(ops, B0, B1, h, w, dtype):
+  """ops.stem_conv against F.conv2d (CPU fp32, the oracle's firstconv[0]) on 16-bit-rounded operands: the kernel multiplies
+  exactly those values and accumulates in fp32, so only summation order and the output rounding differ."""
+  g = torch.Generator().manual_seed(B0 * 100 + h)
+  x0 = torch.randn(B0, 3, h, w, generator=g)
+  x1 = torch.randn(B1, 3, h, w, generator=g) if B1 else None
+  wt = torch.randn(32, 3, 7, 7, generator=g) / math.sqrt(147)
+  sc, sh = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.1
+  out = ops.stem_conv(x0.cuda(), None if x1 is None else x1.cuda(), wt.cuda(), sc.cuda(), sh.cuda(), True, dtype == torch.float16)
+  x = x0 if x1 is None else torch.cat([x0, x1])
+  ref = F.relu(F.conv2d(x.to(dtype).float(), wt.to(dtype).float(), None, 2, 3) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+  assert out.shape == (B0 + B1, (h - 1) // 2 + 1, (w - 1) // 2 + 1, 32) and out.dtype == dtype
+  got = out.float().cpu().permute(0, 3, 1, 2)
+  tol = 2.0 ** (-7 if dtype == torch.bfloat16 else -10)  # one output rounding (+ fp32 summation-order noise)
+  err = (got - ref).abs() / (ref.abs() + 1.0)
+  assert err.max().item() < tol, err.max().item()
+  # no affine / no ReLU variant
+  out2 = ops.stem_conv(x0.cuda(), None, wt.cuda(), None, None, False, dtype == torch.float16).float().cpu().permute(0, 3, 1, 2)
+  ref2 = F.conv2d(x0.to(dtype).float(), wt.to(dtype).float(), None, 2, 3)
+  assert ((out2 - ref2).abs() / (ref2.abs() + 1.0)).max().item() < tol
