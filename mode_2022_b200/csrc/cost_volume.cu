@@ -1,64 +1,80 @@
 // cost_volume.cu -- PSMNet-style concatenation cost volume (reference: models/mode_disparity.py:104-113).
 //
 // Pure data movement, HBM-write bound: per pair at 1024x512/D=192 the kernel reads 2 x 4.19 MB (L2 resident
-// after first touch) and writes 402.65 MB (fp32 NCDHW) or 201.3 MB (bf16 NDHWC).  Every thread produces one
-// 128-bit store; stores are fully coalesced in both layouts.  Shift indices are integers -> bit-exact.
+// after first touch) and writes 402.65 MB (fp32 NCDHW) or 201.3 MB (bf16 NDHWC).  128-bit stores, fully coalesced in
+// both layouts, four per thread in flight.  Shift indices are integers -> bit-exact.
 #include "common.cuh"
 using namespace mode;
 
-// fp32 NCDHW: one thread = 4 consecutive w of one (b, c2, i, h) row.
+// fp32 NCDHW: one CTA = one (b, c2, i) plane of H x W floats, a thread = groups of 4 consecutive w, 4 groups in flight.
 __global__ void __launch_bounds__(256) cost_volume_f32_kernel(const float* __restrict__ ref, const float* __restrict__ tgt,
-                                                              float* __restrict__ cost, int C, int H, int W, int D4, long long total4) {
-  const int W4 = W >> 2;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total4; idx += (long long)gridDim.x * blockDim.x) {
-    int w = (int)(idx % W4) << 2;
-    long long r = idx / W4;
-    int h = (int)(r % H);
-    r /= H;
-    int i = (int)(r % D4);
-    r /= D4;
-    int c2 = (int)(r % (2 * C));
-    int b = (int)(r / (2 * C));
-    float4 v;
-    if (c2 < C) {
-      const float* src = ref + (((size_t)b * C + c2) * H + h) * W + w;
-      float4 s = *reinterpret_cast<const float4*>(src);
-      v.x = (w + 0 >= i) ? s.x : 0.f;
-      v.y = (w + 1 >= i) ? s.y : 0.f;
-      v.z = (w + 2 >= i) ? s.z : 0.f;
-      v.w = (w + 3 >= i) ? s.w : 0.f;
-    } else {
-      const float* src = tgt + (((size_t)b * C + (c2 - C)) * H + h) * W;
-      v.x = (w + 0 >= i) ? __ldg(src + w + 0 - i) : 0.f;
-      v.y = (w + 1 >= i) ? __ldg(src + w + 1 - i) : 0.f;
-      v.z = (w + 2 >= i) ? __ldg(src + w + 2 - i) : 0.f;
-      v.w = (w + 3 >= i) ? __ldg(src + w + 3 - i) : 0.f;
+                                                              float* __restrict__ cost, int C, int H, int W, int D4, long long planes) {
+  const int W4 = W >> 2, per_plane = H * W4;
+  for (long long pl = blockIdx.x; pl < planes; pl += gridDim.x) {
+    const int i = (int)(pl % D4);
+    const long long r = pl / D4;
+    const int c2 = (int)(r % (2 * C)), b = (int)(r / (2 * C));
+    const bool left = c2 < C;
+    const float* src = left ? ref + ((size_t)b * C + c2) * H * W : tgt + ((size_t)b * C + (c2 - C)) * H * W;
+    float4* out = reinterpret_cast<float4*>(cost + (size_t)pl * H * W);
+    for (int e0 = threadIdx.x; e0 < per_plane; e0 += 4 * 256) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < per_plane) {
+          const int h = e / W4, w = (e - h * W4) << 2;
+          const float* s = src + (size_t)h * W + w;
+          if (left) {
+            const float4 q = *reinterpret_cast<const float4*>(s);
+            v[k].x = (w + 0 >= i) ? q.x : 0.f, v[k].y = (w + 1 >= i) ? q.y : 0.f, v[k].z = (w + 2 >= i) ? q.z : 0.f, v[k].w = (w + 3 >= i) ? q.w : 0.f;
+          } else {
+            v[k].x = (w + 0 >= i) ? __ldg(s + 0 - i) : 0.f, v[k].y = (w + 1 >= i) ? __ldg(s + 1 - i) : 0.f;
+            v[k].z = (w + 2 >= i) ? __ldg(s + 2 - i) : 0.f, v[k].w = (w + 3 >= i) ? __ldg(s + 3 - i) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        if (e < per_plane) st_na_v4(out + e, *reinterpret_cast<uint4*>(&v[k]));
+      }
     }
-    st_na_v4(cost + (idx << 2), *reinterpret_cast<uint4*>(&v));
   }
 }
 
-// bf16 NDHWC: voxel = 2C bf16; one thread = one 16-byte chunk (8 channels) of one voxel.
+// 16-bit NDHWC: voxel = 2C channels; one CTA = one (b, disparity i, h) row of W voxels, a thread = 16-byte chunks (8
+// channels) of that row, 4 loads in flight before the first store (no per-element index division: the kernel is a pure
+// HBM-write stream, 201 MB per pair, and every instruction not a load or a store only lowers the bytes in flight).
 __global__ void __launch_bounds__(256) cost_volume_bf16_kernel(const uint16_t* __restrict__ ref, const uint16_t* __restrict__ tgt,
-                                                               uint16_t* __restrict__ cost, int C, int H, int W, int D4, long long total8) {
-  const int chunks = (2 * C) >> 3, half = C >> 3;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total8; idx += (long long)gridDim.x * blockDim.x) {
-    int ch = (int)(idx % chunks);
-    long long r = idx / chunks;
-    int w = (int)(r % W);
-    r /= W;
-    int h = (int)(r % H);
-    r /= H;
-    int i = (int)(r % D4);
-    int b = (int)(r / D4);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (w >= i) {
-      if (ch < half)
-        v = __ldg(reinterpret_cast<const uint4*>(ref + (((size_t)b * H + h) * W + w) * C) + ch);
-      else
-        v = __ldg(reinterpret_cast<const uint4*>(tgt + (((size_t)b * H + h) * W + (w - i)) * C) + (ch - half));
+                                                               uint16_t* __restrict__ cost, int C, int H, int W, int D4, long long rows) {
+  const int chunks = (2 * C) >> 3, half = C >> 3;  // 16-byte chunks per voxel / per feature vector
+  const int per_row = W * chunks;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int h = (int)(row % H);
+    const long long r = row / H;
+    const int i = (int)(r % D4), b = (int)(r / D4);
+    const uint4* rrow = reinterpret_cast<const uint4*>(ref + ((size_t)b * H + h) * W * C);
+    const uint4* trow = reinterpret_cast<const uint4*>(tgt + ((size_t)b * H + h) * W * C);
+    uint4* out = reinterpret_cast<uint4*>(cost + (size_t)row * W * 2 * C);
+    for (int e0 = threadIdx.x; e0 < per_row; e0 += 4 * 256) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        v[k] = make_uint4(0, 0, 0, 0);
+        if (e < per_row) {
+          const int w = e / chunks, ch = e - w * chunks;
+          if (w >= i) v[k] = ch < half ? __ldg(rrow + w * half + ch) : __ldg(trow + (w - i) * half + (ch - half));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        if (e < per_row) st_na_v4(out + e, v[k]);
+      }
     }
-    st_na_v4(cost + (idx << 3), v);
   }
 }
 
@@ -66,9 +82,9 @@ extern "C" int mode_cost_volume_f32(const float* ref, const float* tgt, float* c
   MODE_CHECK_ARG(ref && tgt && cost, "cost_volume_f32: null pointer");
   MODE_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && D4 > 0, "cost_volume_f32: bad shape B=%d C=%d H=%d W=%d D4=%d", B, C, H, W, D4);
   MODE_CHECK_ARG(W % 4 == 0, "cost_volume_f32: W (%d) must be a multiple of 4", W);
-  long long total4 = (long long)B * 2 * C * D4 * H * (W / 4);
-  int blocks = (int)std::min<long long>((total4 + 255) / 256, (long long)kNumSMs * 32);
-  cost_volume_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, tgt, cost, C, H, W, D4, total4);
+  const long long planes = (long long)B * 2 * C * D4;
+  const int blocks = (int)std::min<long long>(planes, (long long)kNumSMs * 16);
+  cost_volume_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, tgt, cost, C, H, W, D4, planes);
   MODE_CHECK_LAUNCH("cost_volume_f32");
   return MODE_OK;
 }
@@ -78,9 +94,9 @@ extern "C" int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mod
   MODE_CHECK_ARG(ref && tgt && cost, "cost_volume_16: null pointer");
   MODE_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && D4 > 0, "cost_volume_16: bad shape B=%d C=%d H=%d W=%d D4=%d", B, C, H, W, D4);
   MODE_CHECK_ARG(C % 8 == 0, "cost_volume_16: C (%d) must be a multiple of 8", C);
-  long long total8 = (long long)B * D4 * H * W * (2 * C / 8);
-  int blocks = (int)std::min<long long>((total8 + 255) / 256, (long long)kNumSMs * 32);
-  cost_volume_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, tgt, cost, C, H, W, D4, total8);
+  const long long rows = (long long)B * D4 * H;
+  const int blocks = (int)std::min<long long>(rows, (long long)kNumSMs * 16);
+  cost_volume_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ref, tgt, cost, C, H, W, D4, rows);
   MODE_CHECK_LAUNCH("cost_volume_16");
   return MODE_OK;
 }

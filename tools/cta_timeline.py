@@ -16,18 +16,21 @@ w = torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), device=de
 wp = ops.conv3d_pack_weights(w, mode)
 for _ in range(3):
   ops.conv3d_bf16(x, wp, co, None, None, res, mode, True, False)
-dbg = torch.zeros(148 * 8 + 4 * 64, dtype=torch.int64, device=dev)
+NMAX = 1024
+dbg = torch.zeros(NMAX * 8 + 4 * 64 + 8 * NMAX, dtype=torch.int64, device=dev)  # room for any grid <= 1024
 lib.mode_conv3d_set_debug_buffer(ctypes.c_void_p(dbg.data_ptr()))
 torch.cuda.synchronize()
 ops.conv3d_bf16(x, wp, co, None, None, res, mode, True, False)
 torch.cuda.synchronize()
 lib.mode_conv3d_set_debug_buffer(ctypes.c_void_p(0))
-st = dbg[148 * 8:].view(4, 64).cpu()
-d = dbg[:148 * 8].view(148, 8).cpu()
+allrec = dbg[:NMAX * 8].view(NMAX, 8).cpu()
+grid = int((allrec[:, 2] != 0).sum().item())  # CTAs that wrote an end time
+d = allrec[:grid]
+st = dbg[grid * 8:grid * 8 + 256].view(4, 64).cpu()
 t0 = d[:, 1].min().item()
 dur = (d[:, 2] - d[:, 1]).float() / 1e3
 start = (d[:, 1] - t0).float() / 1e3
-print('CTAs', d.shape[0], 'distinct SMs', len(set(d[:, 0].tolist())))
+print('CTAs', grid, 'distinct SMs', len(set(d[:, 0].tolist())))
 print('start offset us: min %.1f max %.1f' % (start.min(), start.max()))
 print('duration us: min %.1f median %.1f max %.1f' % (dur.min(), dur.median(), dur.max()))
 print('end us: max %.1f' % ((d[:, 2] - t0).float().max() / 1e3))
@@ -45,7 +48,7 @@ print('dur by smid:')
 print(' '.join('%d:%d' % (a, round(b)) for a, b in bysm))
 
 print('MMA warp cycles: cta, total, wait_tempty, wait_full, in_mma_groups | epilogue warp0 wait_tfull')
-for i in (0, 1, 2, 3, 4, 5, 6, 7, 144, 145, 146, 147):
+for i in (0, 1, 2, 3, 4, 5, 6, 7, grid - 4, grid - 3, grid - 2, grid - 1):
   print(i, d[i, 6].item(), d[i, 4].item(), d[i, 5].item(), d[i, 3].item(), '|', d[i, 7].item())
 
 for c in range(4):
