@@ -71,6 +71,14 @@ int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4
  * scale/shift/residual may be NULL. */
 int mode_sphere_conv_f32(const float* x, const float* pos, const float* w, const float* scale, const float* shift,
                          const float* residual, float* out, int B, int C, int H, int W, int Co, int Kh, int Kw, int relu, void* stream);
+/* ---- a3. spherical convolution backward (fp32, training) ------------------------------------------
+ * replaces sphere_conv_backward_cuda (sphere_conv_cuda.cpp:213-336; Python call sphere_conv.py:57-90) = addmm_ + sphere_col2im
+ * (kernel.cu:293-356) for grad_input, sphere_im2col + addmm_ for grad_weight, addmm_ with ones for grad_bias -- without
+ * the two (C*Kh*Kw, H*W) column buffers.  Layouts as mode_sphere_conv_f32; grad_out (B,Co,H,W).  Like the reference the
+ * three gradients are ACCUMULATED into caller-zeroed buffers (sphere_conv.py:62-64); any of grad_in / grad_w / grad_bias
+ * may be NULL to skip it (x may be NULL when grad_w is, w when grad_in is). */
+int mode_sphere_conv_backward_f32(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w, float* grad_bias,
+                                  int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream);
 /* tensor-core (tcgen05) variant: x (B,H,W,C) NHWC 16-bit, w_packed from mode_sphere_conv_pack_weights,
  * out (B,H,W,Co) 16-bit, fp32 accumulation.  C % 64 == 0, Co in {64,128,192,256}, 3x3. */
 /* gather table = the sampling grid pre-digested once per resolution and 16-bit format (fmt = MODE_FMT_*): per (tap,

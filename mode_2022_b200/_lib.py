@@ -23,6 +23,7 @@ SIGNATURES = {
     'mode_sphere_conv_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _i, _vp],
+    'mode_sphere_conv_backward_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_build_table': [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     'mode_conv3d_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_conv3d_pack_weights': [_vp, _vp, _i, _i, _i, _i, _vp],

@@ -86,10 +86,30 @@ def sphere_conv(input, position, weight, bias=None, stride=1, padding=0, dilatio
   dh, dw = _pair(dilation)
   if (2 * ph - dh * (kh - 1), 2 * pw - dw * (kw - 1)) != (0, 0):
     raise NotImplementedError('sphere_conv: only "same" output size is supported')
-  if input.requires_grad or weight.requires_grad:
-    if torch.is_grad_enabled():
-      raise NotImplementedError('sphere_conv backward is not built yet (SURVEY.md §8f row 1); run under torch.no_grad()')
+  if torch.is_grad_enabled() and (input.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)):
+    return SphereConvFunction.apply(input.float(), position, weight, bias)
   return ops.sphere_conv_f32(input.float(), position, weight, None, bias, None, False)
+
+
+class SphereConvFunction(torch.autograd.Function):
+  """Autograd node of the reference (sphere_conv.py:16-90): forward and backward both go to libmode_b200; gradients flow to
+  input, weight and bias, never to `position` (reference backward returns None for it, sphere_conv.py:89)."""
+
+  @staticmethod
+  def forward(ctx, input, position, weight, bias):
+    ctx.save_for_backward(input, position, weight)
+    ctx.has_bias = bias is not None
+    return ops.sphere_conv_f32(input, position, weight, None, bias, None, False)
+
+  @staticmethod
+  @torch.autograd.function.once_differentiable
+  def backward(ctx, grad_output):
+    input, position, weight = ctx.saved_tensors
+    if not grad_output.is_cuda:
+      raise NotImplementedError  # sphere_conv.py:66-67
+    gi, gw, gb = ops.sphere_conv_backward_f32(input, position, weight, grad_output.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[2],
+                                               ctx.has_bias and ctx.needs_input_grad[3])
+    return gi, None, gw, gb
 
 
 class SphereConv(nn.Module):

@@ -149,6 +149,24 @@ def _(x, pos, weight, scale, shift, residual, relu):
   return x.new_empty((x.shape[0], weight.shape[0], x.shape[2], x.shape[3]))
 
 
+def sphere_conv_backward_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor, need_input: bool, need_weight: bool,
+                             need_bias: bool):
+  """Gradients of sphere_conv_f32 (plain semantics: scale=None, shift=bias): (grad_input, grad_weight, grad_bias), None where
+  not requested.  Mirrors sphere_conv_backward_cuda (sphere_conv_cuda.cpp:213-336): zero-filled buffers, op accumulates."""
+  if not grad_out.is_cuda:
+    raise NotImplementedError  # sphere_conv.py:66-67
+  x, pos, weight, grad_out = (_chk(t, torch.float32, 'sphere_conv_backward') for t in (x, pos, weight, grad_out))
+  B, Cc, H, W = x.shape
+  Co, _, Kh, Kw = weight.shape
+  if grad_out.shape != (B, Co, H, W):
+    raise RuntimeError(f'invalid batch size / shape of grad_output, expected {(B, Co, H, W)}, got {tuple(grad_out.shape)}')  # cpp:107-123
+  gi = torch.zeros_like(x) if need_input else None
+  gw = torch.zeros_like(weight) if need_weight else None
+  gb = torch.zeros(Co, dtype=torch.float32, device=x.device) if need_bias else None
+  _lib.call('mode_sphere_conv_backward_f32', _p(x), _p(pos), _p(weight), _p(grad_out), _p(gi), _p(gw), _p(gb), B, Cc, H, W, Co, Kh, Kw, _stream())
+  return gi, gw, gb
+
+
 def sphere_conv_pack_weights(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
   """(Co,C,3,3) fp32 -> 16-bit weight slabs [tap][C/64][8][Co][8] streamed by the tensor-core kernel."""
   weight = _chk(weight, torch.float32, 'sphere_conv_pack_weights')

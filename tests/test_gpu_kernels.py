@@ -315,3 +315,51 @@ def test_stem_conv_tensor_core(ops, B0, B1, h, w, dtype):
   out2 = ops.stem_conv(x0.cuda(), None, wt.cuda(), None, None, False, dtype == torch.float16).float().cpu().permute(0, 3, 1, 2)
   ref2 = F.conv2d(x0.to(dtype).float(), wt.to(dtype).float(), None, 2, 3)
   assert ((out2 - ref2).abs() / (ref2.abs() + 1.0)).max().item() < tol
+
+
+# ---------------------------------------------------------------------------- a3 sphere conv backward (fp32)
+@pytest.mark.parametrize('B,C,Co,h,w,st,bias', [(1, 1, 1, 5, 10, 'ERP', False), (2, 8, 16, 16, 8, 'Cassini', True), (1, 64, 128, 32, 16, 'Cassini', False),
+                                                (2, 128, 128, 16, 32, 'ERP', True), (1, 5, 33, 16, 8, 'Cassini', True), (1, 70, 40, 40, 20, 'Cassini', False)])
+def test_sphere_conv_backward_vs_oracle_autograd(ops, B, C, Co, h, w, st, bias):
+  """grad_input / grad_weight / grad_bias of the product op against torch autograd through the oracle's restatement
+  (fp64 on CPU), through the reference-shaped autograd node (SphereConvFunction, reference sphere_conv.py:57-90)."""
+  from mode_2022_b200.models.sphere_conv import sphere_conv
+  x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 11)
+  g = torch.Generator().manual_seed(3)
+  bs = torch.randn(Co, generator=g) if bias else None
+  gout = torch.randn(B, Co, h, w, generator=g)
+  xo, wo = x.double().requires_grad_(), wgt.double().requires_grad_()
+  bo = bs.double().requires_grad_() if bias else None
+  O.sphere_conv(xo, pos.double(), wo, bo).backward(gout.double())
+  xc, wc = x.cuda().requires_grad_(), wgt.cuda().requires_grad_()
+  bc = bs.cuda().requires_grad_() if bias else None
+  out = sphere_conv(xc, pos.cuda(), wc, bc, 1, 1, 1, 1)
+  assert out.requires_grad
+  out.backward(gout.cuda())
+  for name, got, ref in (('input', xc.grad, xo.grad), ('weight', wc.grad, wo.grad)) + ((('bias', bc.grad, bo.grad),) if bias else ()):
+    tol = 3e-5 * max(1.0, ref.abs().max().item())
+    err = (got.cpu().double() - ref).abs().max().item()
+    assert err <= tol, (name, err, tol)
+  # only the requested gradients are produced
+  gi, gw, gb = ops.sphere_conv_backward_f32(x.cuda(), pos.cuda(), wgt.cuda(), gout.cuda(), False, True, False)
+  assert gi is None and gb is None and (gw - wc.grad).abs().max().item() <= 3e-5 * max(1.0, wc.grad.abs().max().item())
+
+
+def test_sphere_conv_backward_vs_compiled_reference_op(ops):
+  """Ground truth = the UNMODIFIED reference CUDA op compiled into oracle/_ref (sphere_conv_backward_cuda, cpp:213-336)."""
+  from oracle import build_ref
+  ref = build_ref.load()
+  if ref is None:
+    pytest.skip('oracle/_ref/sphere_conv_cuda.so not built')
+  for (B, C, Co, h, w, st) in [(2, 64, 128, 64, 32, 'Cassini'), (1, 128, 128, 32, 64, 'ERP')]:
+    x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 7)
+    gout = torch.randn(B, Co, h, w, generator=torch.Generator().manual_seed(9))
+    xc, wc, pc, gc = x.cuda(), wgt.cuda(), pos.cuda(), gout.cuda()
+    bias = torch.zeros(Co, device='cuda')
+    gi, gw, gb = torch.zeros_like(xc), torch.zeros_like(wc), torch.zeros_like(bias)
+    ref.sphere_conv_backward_cuda(xc, wc, bias, xc.new_empty(0), pc, xc.new_empty(0), gi, gw, gb, gc, 3, 3, 1, 1, 1, 1, 1, 1, 1, True)
+    torch.cuda.synchronize()
+    pi, pw, pb = ops.sphere_conv_backward_f32(xc, pc, wc, gc, True, True, True)
+    for name, got, want in (('input', pi, gi), ('weight', pw, gw), ('bias', pb, gb)):
+      tol = 5e-5 * max(1.0, want.abs().max().item())
+      assert (got - want).abs().max().item() <= tol, name
