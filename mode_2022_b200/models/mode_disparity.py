@@ -12,8 +12,9 @@ and fp32 logits/regression); `precision='fp16'` runs the same kernels at the sam
 mantissa bits: 8x less rounding noise per stored activation).  Left and right images share the feature
 extractor, so they are run as one batch of 2B.
 
-Only inference is implemented in this round (the backward kernels are SURVEY.md §8f row 1): calling the
-module in training mode raises NotImplementedError rather than silently running something else.
+In training mode (`.train()`) forward returns the three supervised heads (pred1, pred2, pred3) like the reference and is
+differentiable: the spherical layers use libmode_b200's forward and backward kernels, the remaining layers the library
+modules the reference itself trains with.  The fused inference plans are eval-only.
 """
 from __future__ import annotations
 
@@ -40,6 +41,14 @@ class hourglass(nn.Module):
     self.conv5 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes * 2, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
                                nn.BatchNorm3d(inplanes * 2))
     self.conv6 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False), nn.BatchNorm3d(inplanes))
+
+  def forward(self, x, presqu, postsqu):
+    """Training path (reference mode_disparity.py:27-46)."""
+    pre = self.conv2(self.conv1(x))
+    pre = F.relu(pre if postsqu is None else pre + postsqu)
+    out = self.conv4(self.conv3(pre))
+    post = F.relu(self.conv5(out) + (pre if presqu is None else presqu))
+    return self.conv6(post), pre, post
 
 
 class ModeDisparity(nn.Module):
@@ -108,15 +117,14 @@ class ModeDisparity(nn.Module):
 
   # -------------------------------------------------------------------------------------------
   def forward(self, left, right):
-    if self.training:
-      raise NotImplementedError('ModeDisparity (B200): the training graph (backward kernels, SURVEY.md §8f row 1) is not built yet; '
-                                'call .eval() -- there is deliberately no PyTorch fallback')
     if not left.is_cuda:
       raise NotImplementedError('ModeDisparity (B200) runs on CUDA tensors only')
     if left.shape != right.shape or left.dim() != 4 or left.shape[2] % 16 or left.shape[3] % 16:
       raise ValueError('left/right must be (B,3,H,W) with H, W multiples of 16')
     if self.maxdisp % 16:
       raise ValueError('maxdisp must be a multiple of 16')
+    if self.training:
+      return self._forward_train(left, right)
     if self._plan is None:
       self._plan = self._build_plan()
     with torch.no_grad():
@@ -124,3 +132,35 @@ class ModeDisparity(nn.Module):
     if self.out_conf:
       return pred3, conf
     return pred3
+
+  # -------------------------------------------------------------------------------------------
+  def _forward_train(self, left, right):
+    """Training graph (reference mode_disparity.py:99-155): batch-stat BatchNorm, three supervised heads, differentiable end
+    to end in fp32.  The spherical layers run libmode_b200's forward AND backward kernels (SphereConvFunction, SURVEY.md
+    section 8 a3); the cost volume is assembled on the device (the reference zero-fills it on the host and uploads it);
+    everything else is the library code the reference trains with (cuDNN conv / BN / softmax through autograd)."""
+    fl = self.feature_extraction(left.float())
+    fr = self.feature_extraction(right.float())
+    B, Cf, H4, W4 = fl.shape
+    d4 = self.maxdisp // 4
+    cost = fl.new_zeros((B, 2 * Cf, d4, H4, W4))
+    for i in range(d4):  # integer shifts: cost[:, :C, i, :, i:] = ref[..., i:], cost[:, C:, i, :, i:] = tgt[..., :W-i]
+      cost[:, :Cf, i, :, i:] = fl[:, :, :, i:]
+      cost[:, Cf:, i, :, i:] = fr[:, :, :, :W4 - i]
+    cost0 = self.dres0(cost)
+    cost0 = self.dres1(cost0) + cost0
+    out1, pre1, post1 = self.dres2(cost0, None, None)
+    out1 = out1 + cost0
+    out2, _, post2 = self.dres3(out1, pre1, post1)
+    out2 = out2 + cost0
+    out3, _, _ = self.dres4(out2, pre1, post2)  # the third hourglass reuses pre1 (reference :124)
+    out3 = out3 + cost0
+    cost1 = self.classif1(out1)
+    cost2 = self.classif2(out2) + cost1
+    cost3 = self.classif3(out3) + cost2
+    disp = torch.arange(self.maxdisp, device=left.device, dtype=torch.float32).view(1, -1, 1, 1)
+    preds = []
+    for c in (cost1, cost2, cost3):
+      c = F.interpolate(c, [self.maxdisp, left.shape[2], left.shape[3]], mode='trilinear', align_corners=True).squeeze(1)
+      preds.append(torch.sum(F.softmax(c, dim=1) * disp, 1, keepdim=True))
+    return tuple(preds)

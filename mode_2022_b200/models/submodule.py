@@ -1,7 +1,8 @@
 """Building blocks of the stereo network -- same module tree (hence the same state-dict keys) as the
 reference models/submodule.py, so reference checkpoints load unchanged.  The regular 2-D layers are ordinary
 cuDNN-backed nn modules (not a custom-kernel target); the spherical layers and everything
-3-D are executed by libmode_b200 from ModeDisparity.forward, using these modules only as parameter holders.
+3-D are executed by libmode_b200 from ModeDisparity.forward, using these modules only as parameter holders; the
+modules' own forward()s are the differentiable TRAINING path (SphereConv -> libmode_b200 forward/backward kernels).
 """
 from __future__ import annotations
 
@@ -60,6 +61,13 @@ class SphereBasicBlock(nn.Module):
     self.downsample = downsample
     self.stride = stride
 
+  def forward(self, x):
+    """Training path (autograd through SphereConvFunction, libmode_b200 forward + backward kernels); inference goes
+    through ModeDisparity's fused plan instead."""
+    out = self.conv2(self.conv1(x))
+    res = x if self.downsample is None else self.downsample(x)
+    return self.relu(out + res)
+
 
 def bn_affine(bn: nn.modules.batchnorm._BatchNorm):
   """Eval-mode BN as y = x*scale + shift (fp32)."""
@@ -94,3 +102,10 @@ class sphere_feature_extraction(nn.Module):
       layers = [block(inplanes, planes, stride, downsample, pad, dilation)]
       layers += [block(planes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]
     return nn.Sequential(*layers)
+
+  def forward(self, x):
+    """Training path (reference submodule.py:192-201): plain module execution, differentiable end to end."""
+    raw = self.layer2(self.layer1(self.firstconv(x)))
+    reg = self.layer3(raw)
+    sph = self.layer4(reg)
+    return self.lastconv(torch.cat((raw, reg, sph), 1))

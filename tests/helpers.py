@@ -40,3 +40,31 @@ def calibrated_state_dict(H, W, D, st, seed, B=1):
   left, right = synth_inputs(H, W, seed, B)
   sd = O.calibrate_bn(O.synthetic_state_dict(KEY_SHAPES, seed=seed), left, right, D, st)
   return sd, left, right
+
+
+# ---- training-step fixture (oracle/pin_training_against_reference.py writes it, tests/test_gpu_model.py reads it)
+TRAIN_GRAD_KEYS = ['feature_extraction.firstconv.0.0.weight', 'feature_extraction.layer2.0.conv1.0.0.weight', 'feature_extraction.layer4.0.conv1.0.0.weight',
+                   'feature_extraction.layer4.0.conv1.0.1.weight', 'feature_extraction.layer4.2.conv2.0.weight', 'feature_extraction.lastconv.4.0.weight',
+                   'dres0.0.0.weight', 'dres2.conv1.0.0.weight', 'dres3.conv5.0.weight', 'dres4.conv6.0.weight', 'dres4.conv6.1.bias', 'classif1.2.weight',
+                   'classif3.2.weight']
+
+
+def train_inputs(H, W, D, seed, B=2):
+  g = torch.Generator().manual_seed(7000 + seed)
+  left, right = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g)
+  disp_true = torch.rand(B, 1, H, W, generator=g) * (D - 1)
+  mask = torch.rand(B, 1, H, W, generator=g) < 0.8
+  return left, right, disp_true, mask
+
+
+def train_loss(o1, o2, o3, disp_true, mask):
+  """The reference's training loss (train_disparity.py:147-158)."""
+  import torch.nn.functional as F
+  return 0.5 * F.smooth_l1_loss(o1[mask], disp_true[mask]) + 0.7 * F.smooth_l1_loss(o2[mask], disp_true[mask]) + F.smooth_l1_loss(o3[mask], disp_true[mask])
+
+
+def grad_sample(g: torch.Tensor, n=8192):
+  """Every k-th element of a flattened gradient (<= n values): keeps the fixture small; the relative L2 distance over the
+  sample is the statistic compared."""
+  f = g.detach().reshape(-1)
+  return f[::max(1, (f.numel() + n - 1) // n)]

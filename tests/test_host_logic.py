@@ -71,8 +71,11 @@ def test_geometry_host_grids_bit_exact():
     assert np.array_equal(th, tm[:, 0]) and np.array_equal(ph, pm[0])
 
 
-def test_training_mode_fails_loudly():
+def test_cpu_tensors_fail_loudly_in_both_modes():
+  """No CPU / PyTorch fallback: the module refuses CPU tensors in training and in eval mode alike."""
   from mode_2022_b200.models import ModeDisparity
   m = ModeDisparity(16, in_height=64, in_width=32)
-  with pytest.raises(NotImplementedError):
-    m(torch.zeros(1, 3, 64, 32), torch.zeros(1, 3, 64, 32))
+  for mode in (True, False):
+    m.train(mode)
+    with pytest.raises(NotImplementedError):
+      m(torch.zeros(1, 3, 64, 32), torch.zeros(1, 3, 64, 32))
