@@ -99,7 +99,11 @@ class Bf16Plan(_PlanBase):
       c2, b2 = blk.conv2[0], blk.conv2[1]
       ds = _FoldedConv2d(blk.downsample[0], blk.downsample[1], dtype) if blk.downsample is not None else None
       if self.sphere_impl == 'bf16':
-        self.l4.append((c1, ops.sphere_conv_pack_weights(_w(c1), dtype), bn_affine(b1), ops.sphere_conv_pack_weights(_w(c2), dtype), bn_affine(b2), ds))
+        s2, h2 = bn_affine(b2)
+        if ds is not None:  # the downsample branch is only ever added to conv2's pre-activation: its BN shift rides in conv2's
+          h2 = (h2 + ds.shift).contiguous()
+          ds.shift, ds.b = None, None
+        self.l4.append((c1, ops.sphere_conv_pack_weights(_w(c1), dtype), bn_affine(b1), ops.sphere_conv_pack_weights(_w(c2), dtype), (s2, h2), ds))
       else:
         self.l4.append((c1, _w(c1), bn_affine(b1), _w(c2), bn_affine(b2), ds))
 

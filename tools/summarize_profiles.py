@@ -1,0 +1,96 @@
+"""Turn gpurun_out/ evidence (tools/collect_profiles.sh) into the tracked summaries under profiles/."""
+import collections
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, PROF = os.path.join(ROOT, 'gpurun_out'), os.path.join(ROOT, 'profiles')
+TAG = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+
+
+def short(name):
+  name = re.sub(r'\(anonymous namespace\)::|<unnamed>::|void ', '', name)
+  m = re.match(r'([A-Za-z0-9_:]+(<[^(]*>)?)', name)
+  return (m.group(1) if m else name)[:110]
+
+
+def launch_list():
+  rows = list(csv.reader(l for l in open(os.path.join(OUT, 'launches.csv')) if l.startswith('"')))
+  h = rows[0]
+  ik, im, iv, iid = h.index('Kernel Name'), h.index('Metric Name'), h.index('Metric Value'), h.index('ID')
+  iu = h.index('Metric Unit')
+  tscale = {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3, 'nsecond': 1e-6, 'usecond': 1e-3, 'msecond': 1.0, 'second': 1e3}
+  bscale = {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}
+  per = collections.defaultdict(dict)
+  for r in rows[1:]:  # every row carries its own (auto-scaled) unit: normalise to ms / MB
+    val = float(r[iv].replace(',', ''))
+    per[r[iid]]['k'] = short(r[ik])
+    per[r[iid]][r[im]] = val * (tscale[r[iu]] if r[im].startswith('gpu__time') else bscale[r[iu]])
+  agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+  for v in per.values():
+    a = agg[v['k']]
+    a[0] += 1
+    a[1] += v.get('gpu__time_duration.sum', 0)
+    a[2] += v.get('dram__bytes_read.sum', 0)
+    a[3] += v.get('dram__bytes_write.sum', 0)
+  tot = sum(a[1] for a in agg.values())
+  lines = [f'# {TAG} -- ncu launch list (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none`,',
+           '# `python bench.py --steps 2 --warmup 1 --no-graph`, first 1200 launches incl. model setup and warm-up)', '',
+           'Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.', '',
+           f'total launches captured: {len(per)}; total kernel time {tot:.1f} ms', '', '| kernel | launches | total ms | share | dram read MB / launch | dram write MB / launch |', '|---|---:|---:|---:|---:|---:|']
+  for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+    lines.append(f'| `{k}` | {a[0]} | {a[1]:.2f} | {100 * a[1] / tot:.1f}% | {a[2] / a[0]:.1f} | {a[3] / a[0]:.1f} |')
+  conv = [a for k, a in agg.items() if k.startswith('conv3d_tc_kernel')]
+  n = sum(a[0] for a in conv)
+  per_launch = sum(a[2] + a[3] for a in conv) / max(n, 1)
+  lines += ['', f'conv3d_tc_kernel: {n} launches, {sum(a[1] for a in conv):.2f} ms, average DRAM traffic {per_launch:.1f} MB / launch '
+            f'(x 31 launches per step = {per_launch * 31 / 1e3:.2f} GB / step of 6 pairs)']
+  open(os.path.join(PROF, f'{TAG}_launch_list_summary.md'), 'w').write('\n'.join(lines) + '\n')
+  return per_launch
+
+
+KEYS = ['gpu__time_duration.sum', 'sm__cycles_active.avg', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__grid_size', 'launch__block_size',
+        'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic', 'sm__inst_executed.avg.per_cycle_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg',
+        'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct',
+        'lts__t_sector_hit_rate.pct', 'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
+
+
+def full(rep, title, out):
+  path = os.path.join(OUT, rep)
+  if not os.path.exists(path):
+    return
+  txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+  r = list(csv.reader(txt.splitlines()))
+  h, u, v = r[0], r[1], r[2]
+  d = {a.split('TriageCompute.')[-1]: (b, c) for a, b, c in zip(h, u, v)}  # some metrics carry a '<unit>.TriageCompute.' prefix
+  lines = [f'# {TAG} -- ncu --set full --clock-control none: {title}', '', f"kernel: `{short(d.get('Kernel Name', ('', ''))[1])}`", '', '| metric | unit | value |', '|---|---|---|']
+  for k in KEYS:
+    if k in d:
+      lines.append(f'| {k} | {d[k][0]} | {d[k][1]} |')
+  open(os.path.join(PROF, out), 'w').write('\n'.join(lines) + '\n')
+
+
+if __name__ == '__main__':
+  os.makedirs(PROF, exist_ok=True)
+  per_launch = launch_list()
+  full('conv3d_s1_b6.ncu-rep', 'conv3d_tc_kernel<0,32,bf16,32> 32->32 stride 1 @48x256x128, B=6 (dominant kernel)', f'{TAG}_conv3d_tc_s1_ncu.md')
+  full('deconv_b6.ncu-rep', 'conv3d_tc_kernel<2,32,bf16,64> transposed 64->32 @24x128x64 -> 48x256x128, B=6, residual + ReLU', f'{TAG}_conv3d_tc_deconv_ncu.md')
+  full('sphere_b12.ncu-rep', 'sphere_conv_tc_kernel<bf16,128> 128->128 @256x128, B=12, residual + ReLU', f'{TAG}_sphere_conv_tc_ncu.md')
+  full('stem.ncu-rep', 'stem_conv_tc_kernel<bf16> 3->32 7x7 s2 @1024x512, B=12', f'{TAG}_stem_conv_tc_ncu.md')
+  for f, o in (('kernel_timings.txt', f'{TAG}_kernel_timings_b1.txt'), ('conv3d_layer_timings_b6.txt', f'{TAG}_layer_timings_b6.txt')):
+    if os.path.exists(os.path.join(OUT, f)):
+      keep = [l for l in open(os.path.join(OUT, f)) if l.startswith('{') or l.startswith('conv3d_tc') or l.startswith('sphere_conv_tc')]
+      open(os.path.join(PROF, o), 'w').write(''.join(keep))
+  if os.path.exists(os.path.join(OUT, 'bench_final.json')):
+    line = [l for l in open(os.path.join(OUT, 'bench_final.json')) if l.startswith('{')][-1]
+    open(os.path.join(PROF, f'{TAG}_bench_line.json'), 'w').write(line)
+  print('conv3d_tc average DRAM MB per launch: %.1f' % per_launch)
