@@ -193,3 +193,26 @@ def test_training_step_matches_reference_golden():
   with torch.no_grad():
     p = model(left[:1].cuda(), right[:1].cuda())
   assert p.shape == (1, 1, H, W) and torch.isfinite(p).all()
+
+
+def test_host_pipeline_matches_direct_calls():
+  """mode_2022_b200.pipeline.HostPipeline (overlapped H2D / compute / D2H, CUDA graph) returns exactly what direct module
+  calls return, frame by frame, also when more frames are submitted than slots exist."""
+  from mode_2022_b200.pipeline import HostPipeline
+  sd, (H, W, D, st, seed), _ = Hh.golden_state_dict('tiny_cassini')
+  m = _model('tiny_cassini', 'bf16', sd, H, W, D, st)
+  g = torch.Generator().manual_seed(5)
+  frames = [(torch.randn(2, 3, H, W, generator=g).pin_memory(), torch.randn(2, 3, H, W, generator=g).pin_memory()) for _ in range(5)]
+  want = [tuple(t.cpu() for t in m(l.cuda(), r.cuda())) for l, r in frames]
+  for use_graph in (True, False):
+    pipe = HostPipeline(m, 2, H, W, depth=2, use_graph=use_graph)
+    tickets, got = [], []
+    for i, (l, r) in enumerate(frames):
+      tickets.append(pipe.submit(l, r))
+      if i >= 1:
+        got.append(tuple(t.clone() for t in pipe.collect(tickets[i - 1])))
+    got.append(tuple(t.clone() for t in pipe.collect(tickets[-1])))
+    for (p0, c0), (p1, c1) in zip(want, got):
+      assert torch.equal(p0, p1) and torch.equal(c0, c1)
+    with pytest.raises(ValueError):
+      pipe.collect(tickets[0])  # its slot has been reused
