@@ -68,3 +68,12 @@ def grad_sample(g: torch.Tensor, n=8192):
   sample is the statistic compared."""
   f = g.detach().reshape(-1)
   return f[::max(1, (f.numel() + n - 1) // n)]
+
+
+def fusion_inputs(H, W, seed, B=1):
+  """6 depth maps in [0, 20], 6 confidences in [0, 1], 4 RGB images (the shapes ModeFusion.forward takes)."""
+  g = torch.Generator().manual_seed(9000 + seed)
+  depthes = [torch.rand(B, 1, H, W, generator=g) * 20.0 for _ in range(6)]
+  confs = [torch.rand(B, 1, H, W, generator=g) for _ in range(6)]
+  rgbs = [torch.randn(B, 3, H, W, generator=g) for _ in range(4)]
+  return depthes, confs, rgbs

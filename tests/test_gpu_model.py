@@ -216,3 +216,27 @@ def test_host_pipeline_matches_direct_calls():
       assert torch.equal(p0, p1) and torch.equal(c0, c1)
     with pytest.raises(ValueError):
       pipe.collect(tickets[0])  # its slot has been reused
+
+
+@pytest.mark.parametrize('name', ['fusion', 'baseline'])
+def test_fusion_matches_reference_golden(name):
+  """ModeFusion / Baseline forward against the unmodified reference's output (fixture: oracle/pin_fusion_against_reference.py;
+  reference models/mode_fusion.py:91-247) with the same key-addressed synthetic weights and seeded inputs."""
+  import json
+  from mode_2022_b200.models import Baseline, ModeFusion
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  z = np.load(os.path.join(Hh.GOLD, 'mode_fusion_64x32.npz'))
+  shapes = json.load(open(os.path.join(Hh.GOLD, 'mode_fusion_keys.json' if name == 'fusion' else 'baseline_keys.json')))
+  depthes, confs, rgbs = Hh.fusion_inputs(64, 32, 4)
+  cu = lambda ts: [t.cuda() for t in ts]
+  for precision, tol in (('fp32', 2e-4), ('bf16', 0.25)):
+    m = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}, precision=precision) if name == 'fusion' else Baseline(20.0, precision=precision)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == shapes
+    m.load_state_dict(O.synthetic_state_dict(shapes, seed=4))
+    m = m.cuda().eval()
+    with torch.no_grad():
+      y = m(cu(depthes), cu(confs), cu(rgbs)) if name == 'fusion' else m(cu(depthes))
+    assert y.dtype == torch.float32 and y.shape == (1, 1, 64, 32)
+    err = np.abs(y.cpu().numpy() - z[name]).max()
+    assert err <= tol, (precision, err)  # depth units on a [0, 20] range
