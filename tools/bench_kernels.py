@@ -56,7 +56,7 @@ def report(name, ms, bytes_=None, flops=None, **kw):
 
 
 def main():
-  which = sys.argv[1:] or ['cost', 'regress', 'conv3d', 'sphere']
+  which = sys.argv[1:] or ['cost', 'regress', 'conv3d', 'sphere', 'geometry']
   dev = 'cuda'
   D4, H4, W4 = 48, 256, 128
   if 'cost' in which:
@@ -101,6 +101,16 @@ def main():
       wp = ops.sphere_conv_pack_weights(w)
       ms = timeit(lambda: ops.sphere_conv_bf16(xb, pos, wp, 128, None, None, None, False))
       report('sphere_conv_bf16 128->128 @256x128', ms, flops=2 * 128 * 128 * 9 * 256 * 128, bytes_=2 * x.numel() * 2 + pos.numel() * 4)
+
+  if 'geometry' in which:
+    # stage boundary of one frame: 6 pairs, disp -> depth (fp64 triangulation), rotations (grid sample) and the z-buffer warps
+    from mode_2022_b200.utils.geometry import StageBoundary
+    g = torch.Generator().manual_seed(0)
+    disp = (torch.rand(6, 1, 1024, 512, generator=g) * 191).to(dev)
+    conf = torch.rand(6, 1, 1024, 512, generator=g).to(dev)
+    sb = StageBoundary()
+    ms = timeit(lambda: sb(disp, conf), iters=5)
+    report('stage_boundary 6 pairs @1024x512 (disp2depth + rotate/warp, all launches)', ms, bytes_=6 * 4 * 1024 * 512 * 4)
 
 
 if __name__ == '__main__':
