@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
   constexpr int kSetCols = G::ACCS * NT;
   const int R = (MODE == 2) ? 4 : p.tmem_cols / NT;  // mode 2: ring of 4 output planes x 4 parity classes x NT columns
   const uint32_t kTmemCols = (uint32_t)p.tmem_cols;
-  static_assert(4 * 4 * NT <= 512 && 512 / NT <= kMaxSets, "TMEM ring overflow");
+  static_assert((MODE != 2 || 4 * 4 * NT <= 512) && 512 / NT <= kMaxSets, "TMEM ring overflow");
+  constexpr int NTP = NT > 32 ? 32 : NT;  // accumulator columns drained per pass (NT = 64: two passes of 32)
+  constexpr int NPASS = NT / NTP;
 
   // ---- shared memory carve-up: [weights][slots][barriers][tmem ptr]
   uint8_t* w_s = smem;
@@ -674,7 +676,7 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
           ok = oh < p.Ho && ow < p.Wo;
         }
         const size_t vox = (((size_t)it.b * p.Do + od) * p.Ho + oh) * p.Wo + ow;
-        uint4 rpre[NT / 8];
+        uint4 rpre[NTP / 8];
         const float rpre_f32 = (ok && p.res_f32) ? __ldg(p.res_f32 + vox * p.CoReal) : 0.f;
         // lane-contiguous view of this warp's 32 rows x 64 B: instruction k, lane t <-> row 8k + (t >> 2), 16-byte chunk t & 3
         uint8_t* tile_res = epi_s + (size_t)(((cls * 2 + (nplane & 1)) * 4 + (warp & 3)) * 2048);
@@ -695,26 +697,28 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
           }
         } else {
 #pragma unroll
-          for (int q = 0; q < NT / 8; ++q) rpre[q] = (ok && p.res) ? ld_nc_v4(p.res + vox * p.Co + n0 + q * 8) : make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < NTP / 8; ++q) rpre[q] = (ok && p.res) ? ld_nc_v4(p.res + vox * p.Co + n0 + q * 8) : make_uint4(0, 0, 0, 0);
         }
         const long long e0 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(tfull_bar + set), par);
         if (p.dbg) dbg_tfull += clock64() - e0;
         tc_fence_after();
-        {
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ++ps) {
           uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (MODE == 2 ? (uint32_t)(cls * 4 + set) * NT : set * NT);
-          if (NT == 32)
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (MODE == 2 ? (uint32_t)(cls * 4 + set) * NT : set * NT) + ps * 32;
+          const int nn0 = n0 + ps * 32;
+          if (NTP == 32)
             tmem_ld32(taddr, v);
           else
             tmem_ld16(taddr, v);
           tmem_ld_wait();
-          tmem_zero<NT>(taddr);  // hand the block back zeroed (completion awaited below)
+          tmem_zero<NTP>(taddr);  // hand the block back zeroed (completion awaited below)
           if (ok) {
             if (p.out_f32 != nullptr) {
               // classifier: only the first CoReal (=1) channels are real
 #pragma unroll
-              for (int c = 0; c < NT; ++c) {
+              for (int c = 0; c < NTP; ++c) {
                 if (c >= p.CoReal) break;
                 float y = __uint_as_float(v[c]);
                 if (p.scale) y *= __ldg(p.scale + c);
@@ -724,18 +728,18 @@ __global__ void __launch_bounds__(num_threads<MODE>(), MODE == 2 ? 1 : 2) conv3d
                 p.out_f32[vox * p.CoReal + c] = y;
               }
             } else {
-              uint16_t* op = p.out + vox * p.Co + n0;
+              uint16_t* op = p.out + vox * p.Co + nn0;
 #pragma unroll
-              for (int q = 0; q < NT / 8; ++q) {
+              for (int q = 0; q < NTP / 8; ++q) {
                 float y[8];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {  // y = acc * scale + shift (+ residual), two channels per instruction
-                  const float4 sc = ss_s[2 * ((n0 >> 2) + q * 2 + h)], sh = ss_s[2 * ((n0 >> 2) + q * 2 + h) + 1];
+                  const float4 sc = ss_s[2 * ((nn0 >> 2) + q * 2 + h)], sh = ss_s[2 * ((nn0 >> 2) + q * 2 + h) + 1];
                   ffma2(y[4 * h], y[4 * h + 1], __uint_as_float(v[q * 8 + 4 * h]), __uint_as_float(v[q * 8 + 4 * h + 1]), sc.x, sc.y, sh.x, sh.y);
                   ffma2(y[4 * h + 2], y[4 * h + 3], __uint_as_float(v[q * 8 + 4 * h + 2]), __uint_as_float(v[q * 8 + 4 * h + 3]), sc.z, sc.w, sh.z, sh.w);
                 }
                 if (p.res) {
-                  const uint4 r = rpre[q];
+                  const uint4 r = (NPASS == 1) ? rpre[q] : ld_nc_v4(p.res + vox * p.Co + nn0 + q * 8);
                   const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
@@ -834,7 +838,10 @@ __global__ void pack_w3d_kernel(const float* __restrict__ w, uint16_t* __restric
   }
 }
 
-int pick_nt(int Co) { return Co >= 32 ? 32 : 16; }
+// accumulator block width: 32 output channels (Co = 64 runs as two resident blocks on disjoint halves of the grid), 16 for the
+// classifier; the 32 -> 64 stride-2 layer takes all 64 at once (its 110 KB of weights fit: the input is then read once and
+// the depth-stacked MMAs are N = 128 instead of 64, i.e. at the full math rate and long enough to hide the issue bookkeeping)
+int pick_nt(int Ci, int Co, int mode) { return (mode == 1 && Ci == 32 && Co == 64) ? 64 : (Co >= 32 ? 32 : 16); }
 
 // 4-D tensor map over the NDHWC activation: dims (C, W, H, B*D), box {8 ch, WV, HV, 1}; stride-2 layers traverse w/h with
 // element stride 2 (one box per parity).  Out-of-bounds elements (halo outside the volume) are zero-filled by the TMA unit.
@@ -923,8 +930,7 @@ extern "C" int mode_conv3d_set_debug_buffer(void* dev_ptr) {
 }
 
 extern "C" size_t mode_conv3d_packed_weight_elems(int Ci, int Co, int mode) {
-  (void)mode;
-  const int NT = pick_nt(Co);
+  const int NT = pick_nt(Ci, Co, mode);
   const int nblk = (Co + NT - 1) / NT;
   return (size_t)nblk * (Ci / kWHalf) * 27 * 4 * NT * 8;
 }
@@ -934,7 +940,7 @@ extern "C" int mode_conv3d_pack_weights(const float* w, mode_h16* w_packed, int 
   MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_pack_weights: Ci must be 32 or 64 (got %d)", Ci);
   MODE_CHECK_ARG(Co >= 1 && mode >= 0 && mode <= 2, "conv3d_pack_weights: bad Co/mode");
   MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "conv3d_pack_weights: fmt must be 0 (bf16) or 1 (fp16)");
-  const int NT = pick_nt(Co);
+  const int NT = pick_nt(Ci, Co, mode);
   const int nblk = (Co + NT - 1) / NT;
   const long long total = (long long)mode_conv3d_packed_weight_elems(Ci, Co, mode);
   pack_w3d_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, w_packed, Ci, Co, NT, nblk, mode, fmt, total);
@@ -949,7 +955,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
   MODE_CHECK_ARG(x && w_packed && (out || out_f32), "conv3d_tc: null pointer");
   MODE_CHECK_ARG(Ci == 32 || Ci == 64, "conv3d_tc: Ci must be 32 or 64 (got %d)", Ci);
   MODE_CHECK_ARG(B > 0 && Di > 0 && Hi > 0 && Wi > 0 && mode >= 0 && mode <= 2, "conv3d_tc: bad shape/mode");
-  const int NT = pick_nt(Co);
+  const int NT = pick_nt(Ci, Co, mode);
   MODE_CHECK_ARG(out_f32 ? (Co <= 16) : (Co % 32 == 0), "conv3d_tc: Co=%d unsupported (bf16 out needs Co %% 32 == 0, fp32 out needs Co <= 16)", Co);
   MODE_CHECK_ARG(!(mode == 2 && NT != 32), "conv3d_tc: transposed conv needs Co %% 32 == 0");
   TcParams p;
@@ -1029,6 +1035,7 @@ extern "C" int mode_conv3d_tc(const mode_h16* x, const mode_h16* w_packed, const
     const int rc = make_tmap_res(&tmr, residual, fmt, Co, p.Wo, p.Ho, (long long)B * p.Do);
     if (rc != MODE_OK) return rc;
   }
+  if (NT == 64) return launch_tc<1, 64>(p, tm, tmr, SC, fmt, grid, smem, s);
   if (NT == 32) {
     if (mode == 0) return launch_tc<0, 32>(p, tm, tmr, SC, fmt, grid, smem, s);
     if (mode == 1) return launch_tc<1, 32>(p, tm, tmr, SC, fmt, grid, smem, s);
