@@ -99,6 +99,12 @@ int mode_sphere_conv_pack_weights(const float* w /*Co,C,3,3*/, mode_h16* w_packe
  * f32: NCDHW, w in the PyTorch layout ((Co,Ci,3,3,3); transposed: (Ci,Co,3,3,3)).  Di/Hi/Wi are INPUT dims. */
 int mode_conv3d_f32(const float* x, const float* w, const float* scale, const float* shift, const float* residual, float* out,
                     int B, int Ci, int Co, int Di, int Hi, int Wi, int mode, int relu, void* stream);
+/* 32 -> 1 classifier convolution (classif1/2/3[2] = nn.Conv3d(32, 1, 3, padding=1, bias=False), models/mode_disparity.py:72-80)
+ * with the fp32 residual chain cost_k = classif_k(out_k) + cost_{k-1} (:126-129), as a pointwise tensor-core GEMM + shifted
+ * 27-term sum: x (B,D,H,W,32) NDHWC 16-bit, w (1,32,3,3,3) fp32 (rounded to fmt inside), residual_f32 / out_f32 (B,D,H,W)
+ * fp32; residual_f32 may be NULL. */
+int mode_conv3d_classifier_tc(const mode_h16* x, const float* w, const float* residual_f32, float* out_f32, int B, int D, int H, int W, int fmt, void* stream);
+
 /* tensor-core (tcgen05) variant: NDHWC 16-bit activations (fmt), weights pre-packed per tap, fp32 accumulation in TMEM.
  * out_f32 != NULL writes fp32 (B,Do,Ho,Wo,Co) instead of 16-bit (used by the 32->1 classifier, Co <= 16).
  * Ci in {32,64}; Co % 32 == 0 for 16-bit output. */

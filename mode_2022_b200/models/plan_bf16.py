@@ -69,6 +69,7 @@ class Bf16Plan(_PlanBase):
     global _FUSED_CUDNN
     self.dtype = dtype
     self.sphere_impl = 'bf16'
+    self._cls_w = {}
     _FUSED_CUDNN = _probe_fused_cudnn()
     super().__init__(model)
     fe = model.feature_extraction
@@ -166,9 +167,13 @@ class Bf16Plan(_PlanBase):
     return ops.conv3d_bf16(x, wp, cout, scale, shift, residual, mode, relu, False)
 
   def logits(self, x, key, residual):
+    w = getattr(self.model, key.split('.')[0])[2].weight
+    if tuple(w.shape) == (1, 32, 3, 3, 3) and x.shape[-1] == 32:  # pointwise GEMM + shifted sum (conv3d_cls_tc.cu)
+      if key not in self._cls_w:
+        self._cls_w[key] = w.detach().float().contiguous()
+      return ops.conv3d_classifier(x, self._cls_w[key], None if residual is None else residual[..., 0]).unsqueeze(-1)
     wp, cout, _, _, mode = self.p3[key]
-    out = ops.conv3d_bf16(x, wp, cout, None, None, residual, mode, False, True)  # (B, D4, H4, W4, 1) fp32
-    return out
+    return ops.conv3d_bf16(x, wp, cout, None, None, residual, mode, False, True)  # (B, D4, H4, W4, 1) fp32
 
   def run(self, left, right, return_stages=False):
     B, _, H, W = left.shape

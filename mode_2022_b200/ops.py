@@ -339,6 +339,28 @@ def _(x, w_packed, cout, scale, shift, residual, mode, relu, out_f32):
   return torch.empty((B, *conv3d_out_dims(D, H, W, mode), cout), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
 
 
+@torch.library.custom_op('mode_b200::conv3d_classifier', mutates_args=())
+def conv3d_classifier(x: torch.Tensor, weight: torch.Tensor, residual: Optional[torch.Tensor]) -> torch.Tensor:
+  """The 32 -> 1 classifier conv (3x3x3, pad 1, no bias) + fp32 residual as a pointwise tensor-core GEMM + shifted sum.
+  x (B,D,H,W,32) bf16/fp16, weight (1,32,3,3,3) fp32, residual (B,D,H,W) fp32 or None -> (B,D,H,W) fp32."""
+  fmt = _fmt(x.dtype)
+  x = _chk(x, x.dtype, 'conv3d_classifier')
+  weight = _chk(weight, torch.float32, 'conv3d_classifier')
+  if x.dim() != 5 or x.shape[-1] != 32 or tuple(weight.shape) != (1, 32, 3, 3, 3):
+    raise ValueError('conv3d_classifier: expected x (B,D,H,W,32) and weight (1,32,3,3,3)')
+  B, D, H, W, _ = x.shape
+  out = torch.empty((B, D, H, W), dtype=torch.float32, device=x.device)
+  if residual is not None and residual.shape != out.shape:
+    raise RuntimeError('conv3d_classifier: residual shape mismatch')
+  _lib.call('mode_conv3d_classifier_tc', _p(x), _p(weight), _p(_opt(residual, torch.float32, 'residual')), _p(out), B, D, H, W, fmt, _stream())
+  return out
+
+
+@conv3d_classifier.register_fake
+def _(x, weight, residual):
+  return torch.empty(x.shape[:4], dtype=torch.float32, device=x.device)
+
+
 # ------------------------------------------------------------------------------------------------
 # layout helpers
 # ------------------------------------------------------------------------------------------------

@@ -363,3 +363,22 @@ def test_sphere_conv_backward_vs_compiled_reference_op(ops):
     for name, got, want in (('input', pi, gi), ('weight', pw, gw), ('bias', pb, gb)):
       tol = 5e-5 * max(1.0, want.abs().max().item())
       assert (got - want).abs().max().item() <= tol, name
+
+
+# ---------------------------------------------------------------------------- a5 classifier conv (32 -> 1) as pointwise GEMM + shifted sum
+@pytest.mark.parametrize('B,d,h,w', [(1, 4, 16, 8), (2, 5, 20, 12), (1, 48, 32, 24), (1, 3, 40, 72), (2, 17, 16, 8), (1, 1, 16, 8), (3, 2, 24, 8)])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_conv3d_classifier_tensor_core(ops, B, d, h, w, dtype):
+  """ops.conv3d_classifier against F.conv3d (CPU fp32) on the 16-bit-rounded operands (+ fp32 residual): the kernel multiplies
+  exactly those values with fp32 accumulation, so only the summation order differs."""
+  g = torch.Generator().manual_seed(d * 100 + w)
+  x = torch.randn(B, d, h, w, 32, generator=g)
+  wt = torch.randn(1, 32, 3, 3, 3, generator=g) / math.sqrt(27 * 32)
+  res = torch.randn(B, d, h, w, generator=g)
+  xq, wq = x.to(dtype).float(), wt.to(dtype).float()
+  want = F.conv3d(xq.permute(0, 4, 1, 2, 3), wq, None, 1, 1)[:, 0]
+  got = ops.conv3d_classifier(x.to(dtype).cuda(), wt.cuda(), None).cpu()
+  assert got.shape == (B, d, h, w) and got.dtype == torch.float32
+  assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+  got2 = ops.conv3d_classifier(x.to(dtype).cuda(), wt.cuda(), res.cuda()).cpu()
+  assert (got2 - (want + res)).abs().max().item() <= 2e-5 * max(1.0, (want + res).abs().max().item())
