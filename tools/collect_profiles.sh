@@ -4,11 +4,13 @@
 set -x
 O=gpurun_out
 mkdir -p $O
+rm -f $O/conv3d_layer_timings_b6.txt
 python tools/bench_kernels.py > $O/kernel_timings.txt 2>&1
 for c in 64,32,48,256,128,0 32,32,48,256,128,0 32,64,48,256,128,1 64,64,24,128,64,0 64,64,24,128,64,1 64,64,12,64,32,0 64,64,12,64,32,2 64,32,24,128,64,2; do
   NORES=1 CFG=$c BATCH=6 python tools/deconv_one.py >> $O/conv3d_layer_timings_b6.txt 2>&1
 done
 python tools/sphere_one.py >> $O/conv3d_layer_timings_b6.txt 2>&1
+python tools/cls_one.py >> $O/conv3d_layer_timings_b6.txt 2>&1
 # launch list of the bench command (eager launches so that every kernel is a separate ncu record)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1200 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-graph > $O/bench_under_ncu.log 2>&1
