@@ -225,9 +225,12 @@ def run_ours(args):
       t_conv = sum(sum(by.get(k, [])) for k in conv_names) / 3.0  # ms per step in the conv3d kernels
       n_conv = sum(len(by.get(k, [])) for k in conv_names) // 3
       pk = peaks()
-      flops = CONV3D_GFLOP_PER_PAIR * 1e9 * PAIRS
+      # dres0[0] (64 -> 32 on the cost volume, 2*27*64*32*48*256*128 = 173.9 GFLOP / pair) does not run as a conv3d kernel when it is
+      # fused with the cost volume (costvol_conv.cu: two small GEMMs + a write-bound kernel): its FLOPs leave the numerator too
+      fused_first = 'mode_costvol_conv_fused' in by
+      flops = (CONV3D_GFLOP_PER_PAIR - (173.9 if fused_first else 0.0)) * 1e9 * PAIRS
       ach = flops / (t_conv * 1e-3) / 1e12 if t_conv > 0 else 0.0
-      roof = {'bound': 'tensor', 'kernel': 'conv3d_tc_kernel + conv3d_cls_tc_kernel (25 conv3d/deconv3d launches per step + 3 classifier launches = the 28 layers of the 3-D stack)', 'achieved': round(ach, 1),
+      roof = {'bound': 'tensor', 'kernel': 'conv3d_tc_kernel + conv3d_cls_tc_kernel (24 conv3d/deconv3d launches per step + 3 classifier launches; the first layer of the 3-D stack is fused with the cost volume)' if fused_first else 'conv3d_tc_kernel + conv3d_cls_tc_kernel (28 layers of the 3-D stack)', 'achieved': round(ach, 1),
               'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['bf16_tflops_sustained'], 3), 'traffic': CONV3D_DRAM_BYTES_PER_STEP,
               'traffic_note': 'DRAM read+write bytes of the 28 conv3d launches of one step (6 pairs), ncu launch list profiles/r01_launch_list_summary.md',
               'peak_source': pk['source'] + ' (sustained bf16; burst %.0f)' % pk['bf16_tflops'], 'launches_per_step': n_conv,

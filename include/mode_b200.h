@@ -55,6 +55,17 @@ int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mode_h16* cost
 int mode_stem_conv_tc(const float* x0, const float* x1, const float* w, const float* scale, const float* shift, mode_h16* out, int B0, int B1, int H, int W,
                       int relu, int fmt, void* stream);
 
+/* ---- a4+a5. cost volume fused into the first 3-D convolution --------------------------------------
+ * replaces the cost-volume build (models/mode_disparity.py:104-113) AND dres0[0] = convbn_3d(64, 32, 3, 1, 1) + ReLU (:66, :115)
+ * without materialising the volume.  ur / ut: per-(kd,kw) column responses of the two feature maps, (B*H*W, 9, 32) fp32,
+ * ur[p][kd*3+kw][o] = sum_{c,kh} W[o,c,kd,kh,kw] * ref[c, h-1+kh, w] (ut: W[o,32+c,...] and tgt) -- one library GEMM each
+ * (K = 96, N = 288).  out (B, D4, H, W, 32) NDHWC 16-bit =
+ * act(conv3d(cost) * scale + shift).  Exact (see costvol_conv.cu); differs from cost_volume + conv3d_tc by fp32 summation order. */
+/* GEMM operand of those column responses: cols (B*H*W, 96) 16-bit, cols[(b,h,w)][kh*32 + c] = f[b, h-1+kh, w, c] (f NHWC, 32 ch). */
+int mode_costvol_cols(const mode_h16* f, mode_h16* cols, int B, int H, int W, void* stream);
+int mode_costvol_conv_fused(const float* ur, const float* ut, const float* scale, const float* shift, mode_h16* out, int B, int D4, int H, int W, int relu, int fmt,
+                            void* stream);
+
 /* ---- a6/a7. trilinear upsample + softmax + soft-argmin (+ confidence) --------------------------
  * replaces models/mode_disparity.py:143-152 (+131-141 for the training heads), :157-183 and
  * models/submodule.py:50-57.  cost: (B, D4, H4, W4) fp32 -> pred (B, H, W) [, conf (B, H, W) or NULL].

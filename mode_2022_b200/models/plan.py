@@ -52,9 +52,14 @@ class _PlanBase:
     out = c(post, f'{name}.conv6', relu=False, residual=c0)  # "+ cost0" of mode_disparity.py:119,122,125 fused
     return out, pre, post
 
-  def regularise(self, cost):
+  def first3d(self, fl, fr, d4):
+    """Cost volume + dres0[0] (reference mode_disparity.py:104-115); returns (cost or None, activation)."""
+    cost = self.cost_volume(fl, fr, d4)
+    return cost, self.conv3d(cost, 'dres0.0', relu=True)
+
+  def regularise(self, c0):
+    """3-D stack from the output of dres0[0] on."""
     c = self.conv3d
-    c0 = c(cost, 'dres0.0', relu=True)
     c0 = c(c0, 'dres0.2', relu=True)
     t = c(c0, 'dres1.0', relu=True)
     c0 = c(t, 'dres1.2', relu=False, residual=c0)
@@ -69,8 +74,8 @@ class _PlanBase:
   def run(self, left, right, return_stages=False):
     B, _, H, W = left.shape
     feat = self.features(torch.cat([left, right], 0))
-    cost = self.cost_volume(feat[:B], feat[B:], self.maxdisp // 4)
-    cost1, cost2, cost3 = self.regularise(cost)
+    cost, c0 = self.first3d(feat[:B], feat[B:], self.maxdisp // 4)
+    cost1, cost2, cost3 = self.regularise(c0)
     pred, conf = ops.disp_regress(cost3, self.maxdisp, H, W)
     if return_stages:
       return pred, conf, dict(feat=feat, cost=cost, cost1=cost1, cost2=cost2, cost3=cost3)

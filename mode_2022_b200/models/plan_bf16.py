@@ -5,6 +5,8 @@ bits (8x smaller rounding error per stored activation), which is what brings the
 on un-trained networks (measured: bf16 0.03 px, fp16 0.004 px)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -70,6 +72,7 @@ class Bf16Plan(_PlanBase):
     self.dtype = dtype
     self.sphere_impl = 'bf16'
     self._cls_w = {}
+    self._cv_w = None
     _FUSED_CUDNN = _probe_fused_cudnn()
     super().__init__(model)
     fe = model.feature_extraction
@@ -162,6 +165,18 @@ class Bf16Plan(_PlanBase):
     fl, fr = fl.permute(0, 2, 3, 1), fr.permute(0, 2, 3, 1)  # NHWC views
     return ops.cost_volume(fl.contiguous(), fr.contiguous(), d4)  # (B, D4, H4, W4, 64) bf16
 
+  def first3d(self, fl, fr, d4):
+    """Cost volume + dres0[0] fused (costvol_conv.cu): the 64-channel volume is never written.  Falls back to the two-kernel
+    path for feature widths other than 32."""
+    conv = self.model.dres0[0][0]
+    if fl.shape[1] != 32 or tuple(conv.weight.shape) != (32, 64, 3, 3, 3) or os.environ.get('MODE_B200_NO_COSTVOL_FUSION'):
+      return super().first3d(fl, fr, d4)
+    if self._cv_w is None:
+      self._cv_w = ops.costvol_conv_weights(_w(conv), self.dtype)
+    _, _, scale, shift, _ = self.p3['dres0.0']
+    fl, fr = fl.permute(0, 2, 3, 1).contiguous(), fr.permute(0, 2, 3, 1).contiguous()  # NHWC views of the channels_last features
+    return None, ops.costvol_conv(fl, fr, self._cv_w[0], self._cv_w[1], scale, shift, d4, True)
+
   def conv3d(self, x, key, relu, residual=None):
     wp, cout, scale, shift, mode = self.p3[key]
     return ops.conv3d_bf16(x, wp, cout, scale, shift, residual, mode, relu, False)
@@ -178,8 +193,8 @@ class Bf16Plan(_PlanBase):
   def run(self, left, right, return_stages=False):
     B, _, H, W = left.shape
     feat = self.features(left, right)
-    cost = self.cost_volume(feat[:B], feat[B:], self.maxdisp // 4)
-    cost1, cost2, cost3 = self.regularise(cost)
+    cost, c0 = self.first3d(feat[:B], feat[B:], self.maxdisp // 4)
+    cost1, cost2, cost3 = self.regularise(c0)
     pred, conf = ops.disp_regress(cost3[..., 0], self.maxdisp, H, W)
     if return_stages:
       return pred, conf, dict(feat=feat, cost=cost, cost1=cost1[..., 0], cost2=cost2[..., 0], cost3=cost3[..., 0])

@@ -86,6 +86,48 @@ def _(ref, tgt, d4):
   return ref.new_empty((B, d4, H, W, 2 * Cc))
 
 
+def costvol_conv_weights(weight: torch.Tensor, dtype=torch.bfloat16):
+  """dres0[0] weight (32, 64, 3, 3, 3) fp32 -> the two (96, 288) GEMM operands of costvol_conv: row kh*32 + c, column
+  (kd*3 + kw)*32 + o, rounded to the 16-bit storage format exactly like the implicit-GEMM weights."""
+  weight = _chk(weight, torch.float32, 'costvol_conv_weights')
+  if tuple(weight.shape) != (32, 64, 3, 3, 3):
+    raise ValueError('costvol_conv_weights: expected (32, 64, 3, 3, 3)')
+  halves = []
+  for w in (weight[:, :32], weight[:, 32:]):
+    halves.append(w.permute(3, 1, 2, 4, 0).reshape(96, 288).to(dtype).contiguous())  # (kh, c, kd, kw, o)
+  return halves[0], halves[1]
+
+
+@torch.library.custom_op('mode_b200::costvol_conv', mutates_args=())
+def costvol_conv(ref: torch.Tensor, tgt: torch.Tensor, wr: torch.Tensor, wt: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], d4: int,
+                 relu: bool) -> torch.Tensor:
+  """Cost volume + first 3-D conv (64 -> 32) + affine + ReLU without materialising the volume (costvol_conv.cu).
+  ref / tgt (B,H,W,32) NHWC 16-bit features, wr / wt from costvol_conv_weights -> (B, d4, H, W, 32) NDHWC 16-bit."""
+  fmt = _fmt(ref.dtype)
+  ref, tgt = _chk(ref, ref.dtype, 'costvol_conv'), _chk(tgt, ref.dtype, 'costvol_conv')
+  wr, wt = _chk(wr, ref.dtype, 'costvol_conv'), _chk(wt, ref.dtype, 'costvol_conv')
+  if ref.dim() != 4 or ref.shape != tgt.shape or ref.shape[-1] != 32 or tuple(wr.shape) != (96, 288) or tuple(wt.shape) != (96, 288):
+    raise ValueError('costvol_conv: expected (B,H,W,32) features and (96,288) weight matrices')
+  B, H, W, _ = ref.shape
+
+  def cols(f):  # (B,H,W,32) -> (B*H*W, 96): channels of rows h-1, h, h+1 (zero rows outside)
+    c = torch.empty((B * H * W, 96), dtype=f.dtype, device=f.device)
+    _lib.call('mode_costvol_cols', _p(f), _p(c), B, H, W, _stream())
+    return c
+
+  ur = torch.mm(cols(ref), wr, out_dtype=torch.float32)  # library GEMMs, fp32 accumulate and output
+  ut = torch.mm(cols(tgt), wt, out_dtype=torch.float32)
+  out = torch.empty((B, d4, H, W, 32), dtype=ref.dtype, device=ref.device)
+  _lib.call('mode_costvol_conv_fused', _p(ur), _p(ut), _p(_opt(scale, torch.float32, 'scale')), _p(_opt(shift, torch.float32, 'shift')), _p(out), B, d4,
+            H, W, int(relu), fmt, _stream())
+  return out
+
+
+@costvol_conv.register_fake
+def _(ref, tgt, wr, wt, scale, shift, d4, relu):
+  return torch.empty((ref.shape[0], d4, ref.shape[1], ref.shape[2], 32), dtype=ref.dtype, device=ref.device)
+
+
 # ------------------------------------------------------------------------------------------------
 # a6/a7. regression + confidence
 # ------------------------------------------------------------------------------------------------

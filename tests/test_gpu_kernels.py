@@ -382,3 +382,30 @@ def test_conv3d_classifier_tensor_core(ops, B, d, h, w, dtype):
   assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
   got2 = ops.conv3d_classifier(x.to(dtype).cuda(), wt.cuda(), res.cuda()).cpu()
   assert (got2 - (want + res)).abs().max().item() <= 2e-5 * max(1.0, (want + res).abs().max().item())
+
+
+# ---------------------------------------------------------------------------- a4+a5 cost volume fused into dres0[0]
+@pytest.mark.parametrize('B,h,w,d4', [(1, 8, 16, 4), (2, 16, 24, 12), (1, 4, 8, 8), (1, 32, 128, 48), (2, 3, 40, 1), (1, 5, 6, 6)])
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float16])
+def test_costvol_conv_fused(ops, B, h, w, d4, dtype):
+  """ops.costvol_conv (no volume materialised) against the literal definition: oracle cost volume + F.conv3d in fp64 on the
+  16-bit-rounded operands (exact products, so only fp32 summation order and the output rounding differ), and against the
+  product's own two-kernel path (cost_volume + conv3d_bf16)."""
+  g = torch.Generator().manual_seed(h * 10 + d4)
+  ref, tgt = torch.randn(B, 32, h, w, generator=g), torch.randn(B, 32, h, w, generator=g)
+  wt = torch.randn(32, 64, 3, 3, 3, generator=g) / math.sqrt(27 * 64)
+  sc, sh = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.2
+  rq, tq, wq = ref.to(dtype).double(), tgt.to(dtype).double(), wt.to(dtype).double()
+  cost = O.cost_volume(rq, tq, d4)
+  want = F.relu(F.conv3d(cost, wq, None, 1, 1) * sc.double().view(1, -1, 1, 1, 1) + sh.double().view(1, -1, 1, 1, 1))  # (B,32,d4,h,w)
+  nhwc = lambda t: t.to(dtype).permute(0, 2, 3, 1).contiguous().cuda()
+  wr, wtm = ops.costvol_conv_weights(wt.cuda(), dtype)
+  got = ops.costvol_conv(nhwc(ref), nhwc(tgt), wr, wtm, sc.cuda(), sh.cuda(), d4, True)
+  assert got.shape == (B, d4, h, w, 32) and got.dtype == dtype
+  gotc = got.float().cpu().permute(0, 4, 1, 2, 3).double()
+  tol = 2.0 ** (-8 if dtype == torch.bfloat16 else -11)  # one output rounding
+  assert ((gotc - want).abs() / (want.abs() + 1.0)).max().item() <= tol
+  # the two-kernel product path gives the same values up to fp32 summation order (i.e. at most one 16-bit ulp apart)
+  vol = ops.cost_volume(nhwc(ref), nhwc(tgt), d4)
+  two = ops.conv3d_bf16(vol, ops.conv3d_pack_weights(wt.cuda(), 0, dtype), 32, sc.cuda(), sh.cuda(), None, 0, True, False)
+  assert ((got.float() - two.float()).abs() / (two.float().abs() + 1.0)).max().item() <= 2 * tol

@@ -95,10 +95,10 @@ def test_h16_conv3d_stack_epe(name, precision):
   with torch.no_grad():
     feat = p32.features(torch.cat([left, right]).cuda())
     cost = p32.cost_volume(feat[:1], feat[1:], D // 4)
-    _, _, c3 = p32.regularise(cost)
+    _, _, c3 = p32.regularise(p32.conv3d(cost, 'dres0.0', relu=True))
     pred32, _ = ops.disp_regress(c3, D, H, W)
     cost_b = ops.nchw_f32_to_nhwc_bf16(cost, dtype)
-    _, _, c3b = pbf.regularise(cost_b)
+    _, _, c3b = pbf.regularise(pbf.conv3d(cost_b, 'dres0.0', relu=True))
     predbf, _ = ops.disp_regress(c3b[..., 0], D, H, W)
   epe = _epe(predbf.cpu().numpy(), pred32.cpu().numpy())
   print(f'{name}: {precision} conv3d stack EPE vs fp32 stack = {epe:.5f} px; max {np.abs(predbf.cpu().numpy() - pred32.cpu().numpy()).max():.4f}')
