@@ -33,9 +33,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 H, W, MAXDISP, PAIRS = 1024, 512, 192, 6
-# measured once with ncu (profiles/r01_launch_list_summary.md): 712.4 MB average DRAM traffic per conv3d launch x 28 launches per step;
+# measured once with ncu (profiles/r01_launch_list_summary.md): 676.1 MB average DRAM traffic per conv3d launch x 27 launches per step;
 # the dominant 32->32 layer moves 1.16 GB against 1.21 GB of algorithmic input + output bytes (profiles/r01_conv3d_tc_s1_ncu.md)
-CONV3D_DRAM_BYTES_PER_STEP = 19.95e9
+CONV3D_DRAM_BYTES_PER_STEP = 18.25e9
 CONV3D_GFLOP_PER_PAIR = 1013.8  # 22 conv3d + 6 deconv3d at 1024x512, D=192
 WORKLOAD = 'ModeDisparity stereo stage, 6 camera pairs/step, Cassini 1024x512 (=512x1024 ERP), maxdisp=192, out_conf'
 
@@ -232,7 +232,7 @@ def run_ours(args):
       ach = flops / (t_conv * 1e-3) / 1e12 if t_conv > 0 else 0.0
       roof = {'bound': 'tensor', 'kernel': 'conv3d_tc_kernel + conv3d_cls_tc_kernel (24 conv3d/deconv3d launches per step + 3 classifier launches; the first layer of the 3-D stack is fused with the cost volume)' if fused_first else 'conv3d_tc_kernel + conv3d_cls_tc_kernel (28 layers of the 3-D stack)', 'achieved': round(ach, 1),
               'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['bf16_tflops_sustained'], 3), 'traffic': CONV3D_DRAM_BYTES_PER_STEP,
-              'traffic_note': 'DRAM read+write bytes of the 28 conv3d launches of one step (6 pairs), ncu launch list profiles/r01_launch_list_summary.md',
+              'traffic_note': 'DRAM read+write bytes of the 27 conv3d launches of one step (6 pairs), ncu launch list profiles/r01_launch_list_summary.md',
               'peak_source': pk['source'] + ' (sustained bf16; burst %.0f)' % pk['bf16_tflops'], 'launches_per_step': n_conv,
               'ms_per_step_in_kernel': round(t_conv, 3),
               'other_kernels_ms_per_step': {k: round(sum(v) / 3.0, 3) for k, v in by.items() if k not in conv_names}}

@@ -11,6 +11,7 @@ for c in 64,32,48,256,128,0 32,32,48,256,128,0 32,64,48,256,128,1 64,64,24,128,6
 done
 python tools/sphere_one.py >> $O/conv3d_layer_timings_b6.txt 2>&1
 python tools/cls_one.py >> $O/conv3d_layer_timings_b6.txt 2>&1
+python tools/costvol_one.py >> $O/conv3d_layer_timings_b6.txt 2>&1
 # launch list of the bench command (eager launches so that every kernel is a separate ncu record)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1200 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-graph > $O/bench_under_ncu.log 2>&1

@@ -48,7 +48,7 @@ def launch_list():
   n = sum(a[0] for a in conv)
   per_launch = sum(a[2] + a[3] for a in conv) / max(n, 1)
   lines += ['', f'conv3d_tc_kernel + conv3d_cls_tc_kernel: {n} launches, {sum(a[1] for a in conv):.2f} ms, average DRAM traffic {per_launch:.1f} MB / launch '
-            f'(x 28 launches per step = {per_launch * 28 / 1e3:.2f} GB / step of 6 pairs)']
+            f'(x 27 launches per step = {per_launch * 27 / 1e3:.2f} GB / step of 6 pairs)']
   open(os.path.join(PROF, f'{TAG}_launch_list_summary.md'), 'w').write('\n'.join(lines) + '\n')
   return per_launch
 
@@ -88,7 +88,7 @@ if __name__ == '__main__':
   full('stem.ncu-rep', 'stem_conv_tc_kernel<bf16> 3->32 7x7 s2 @1024x512, B=12', f'{TAG}_stem_conv_tc_ncu.md')
   for f, o in (('kernel_timings.txt', f'{TAG}_kernel_timings_b1.txt'), ('conv3d_layer_timings_b6.txt', f'{TAG}_layer_timings_b6.txt')):
     if os.path.exists(os.path.join(OUT, f)):
-      keep = [l for l in open(os.path.join(OUT, f)) if l.startswith(('{', 'conv3d_tc', 'sphere_conv_tc', 'pointwise', 'implicit-gemm'))]
+      keep = [l for l in open(os.path.join(OUT, f)) if l.startswith(('{', 'conv3d_tc', 'sphere_conv_tc', 'pointwise', 'implicit-gemm', 'fused', 'cost_volume +'))]
       open(os.path.join(PROF, o), 'w').write(''.join(keep))
   if os.path.exists(os.path.join(OUT, 'bench_final.json')):
     line = [l for l in open(os.path.join(OUT, 'bench_final.json')) if l.startswith('{')][-1]
