@@ -26,3 +26,12 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def gold_dir():
   return GOLD
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_rng():
+  """Every test starts from the same global RNG state (CPU and CUDA): a few tests draw unseeded tensors, and statistical
+  bounds (max over ~1e5 outputs of a random-walk rounding error) must not depend on what ran before."""
+  import torch
+  torch.manual_seed(20221017)
+  yield

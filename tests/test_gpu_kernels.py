@@ -274,8 +274,9 @@ def test_conv3d_bf16_classifier_fp32_out(ops):
 def test_sphere_conv_bf16_tensor_core(ops, B, C, Co, h, w, st, dtype):
   x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 21)
   xq, wq = x.to(dtype), wgt.to(dtype)
-  scale, shift = torch.rand(Co) + 0.5, torch.randn(Co)
-  res = torch.randn(B, Co, h, w).to(dtype)
+  g = torch.Generator().manual_seed(1000 * B + Co + h)  # seeded: the bound below is statistical (max over ~1e5 outputs of a random-walk error)
+  scale, shift = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g)
+  res = torch.randn(B, Co, h, w, generator=g).to(dtype)
   want = F.relu(O.sphere_conv(xq.float(), pos, wq.float()) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float())
   wp = ops.sphere_conv_pack_weights(wgt.cuda(), dtype)
   got = ops.sphere_conv_bf16(xq.permute(0, 2, 3, 1).contiguous().cuda(), pos.cuda(), wp, Co, scale.cuda(), shift.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), True)
