@@ -90,8 +90,8 @@ def main():
       out_vox = vox_in if mode == 0 else (vox_in // 8 if mode == 1 else vox_in * 8)
       report('conv3d_bf16 ' + name, ms, flops=flops, bytes_=vox_in * ci * 2 + out_vox * co * (4 if f32 else 2))
   if 'sphere' in which:
-    from oracle import mode_oracle as O
-    pos = torch.from_numpy(O.gen_sphere_position(256, 128, 'Cassini')).to(dev)
+    from mode_2022_b200.models.sphere_conv import sphere_position_numpy
+    pos = torch.from_numpy(sphere_position_numpy(128, 256, 'Cassini')).to(dev)
     x = torch.randn(1, 128, 256, 128, device=dev)
     w = torch.randn(128, 128, 3, 3, device=dev) / 34
     ms = timeit(lambda: ops.sphere_conv_f32(x, pos, w, None, None, None, False), iters=5)

@@ -3,11 +3,11 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mode_2022_b200 import ops
-from oracle import mode_oracle as O
+from mode_2022_b200.models.sphere_conv import sphere_position_numpy
 dev = 'cuda'
 B = int(os.environ.get('BATCH', '12'))
 dt = torch.float16 if os.environ.get('FP16') else torch.bfloat16
-pos = torch.from_numpy(O.gen_sphere_position(256, 128, 'Cassini')).to(dev)
+pos = torch.from_numpy(sphere_position_numpy(128, 256, 'Cassini')).to(dev)
 x = torch.randn(B, 256, 128, 128, device=dev).to(dt)
 res = torch.randn(B, 256, 128, 128, device=dev).to(dt)
 w = torch.randn(128, 128, 3, 3, device=dev) / 34
