@@ -85,6 +85,8 @@ if __name__ == '__main__':
   full('conv3d_s1_b6.ncu-rep', 'conv3d_tc_kernel<0,32,bf16,32> 32->32 stride 1 @48x256x128, B=6 (dominant kernel)', f'{TAG}_conv3d_tc_s1_ncu.md')
   full('deconv_b6.ncu-rep', 'conv3d_tc_kernel<2,32,bf16,64> transposed 64->32 @24x128x64 -> 48x256x128, B=6, residual + ReLU', f'{TAG}_conv3d_tc_deconv_ncu.md')
   full('sphere_b12.ncu-rep', 'sphere_conv_tc_kernel<bf16,128> 128->128 @256x128, B=12, residual + ReLU', f'{TAG}_sphere_conv_tc_ncu.md')
+  full('costvol.ncu-rep', 'costvol_conv_kernel<bf16> cost volume fused into dres0[0], B=6, 256x128 features, D/4=48', f'{TAG}_costvol_conv_ncu.md')
+  full('cls.ncu-rep', 'conv3d_cls_tc_kernel<bf16> 32->1 classifier, B=6, 48x256x128', f'{TAG}_conv3d_cls_tc_ncu.md')
   full('stem.ncu-rep', 'stem_conv_tc_kernel<bf16> 3->32 7x7 s2 @1024x512, B=12', f'{TAG}_stem_conv_tc_ncu.md')
   for f, o in (('kernel_timings.txt', f'{TAG}_kernel_timings_b1.txt'), ('conv3d_layer_timings_b6.txt', f'{TAG}_layer_timings_b6.txt')):
     if os.path.exists(os.path.join(OUT, f)):
