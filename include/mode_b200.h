@@ -130,6 +130,9 @@ int mode_conv3d_set_debug_buffer(void* dev_ptr);
 /* ---- layout helpers (NCHW fp32 <-> NHWC 16-bit), used at the cuDNN / custom-kernel seams ---------- */
 int mode_nchw_f32_to_nhwc_16(const float* x, mode_h16* y, int B, int C, int HW, int fmt, void* stream);
 int mode_nhwc_16_to_nchw_f32(const mode_h16* x, float* y, int B, int C, int HW, int fmt, void* stream);
+/* channel concatenation of three NHWC 16-bit maps (torch.cat((raw, regular, sphere), 1) in front of lastconv, models/submodule.py:198):
+ * a (npix, Ca), b (npix, Cb), c (npix, Cc) -> out (npix, Ca+Cb+Cc); channel counts multiples of 8. */
+int mode_concat3_nhwc_16(const mode_h16* a, const mode_h16* b, const mode_h16* c, mode_h16* out, long long npix, int Ca, int Cb, int Cc, void* stream);
 
 /* ---- a8. disparity -> depth ----------------------------------------------------------------------
  * replaces disp2depth's triangulation, save_output_disparity_stage.py:118-133 (fp64 arithmetic on fp32 inputs,

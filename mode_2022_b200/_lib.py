@@ -33,6 +33,7 @@ SIGNATURES = {
     'mode_conv3d_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_nchw_f32_to_nhwc_16': [_vp, _vp, _i, _i, _i, _i, _vp],
     'mode_nhwc_16_to_nchw_f32': [_vp, _vp, _i, _i, _i, _i, _vp],
+    'mode_concat3_nhwc_16': [_vp, _vp, _vp, _vp, C.c_longlong, _i, _i, _i, _vp],
     'mode_disp_to_depth': [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],

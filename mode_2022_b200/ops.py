@@ -434,6 +434,20 @@ def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
   return y
 
 
+def concat3_nhwc(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+  """Channel concatenation of three NHWC 16-bit maps (B,H,W,Ca|Cb|Cc) -> (B,H,W,Ca+Cb+Cc): a streaming copy kernel."""
+  a = _chk(a, a.dtype, 'concat3_nhwc')
+  b, c = _chk(b, a.dtype, 'concat3_nhwc'), _chk(c, a.dtype, 'concat3_nhwc')
+  if a.shape[:-1] != b.shape[:-1] or a.shape[:-1] != c.shape[:-1]:
+    raise ValueError('concat3_nhwc: leading dimensions differ')
+  out = torch.empty((*a.shape[:-1], a.shape[-1] + b.shape[-1] + c.shape[-1]), dtype=a.dtype, device=a.device)
+  npix = 1
+  for s in a.shape[:-1]:
+    npix *= s
+  _lib.call('mode_concat3_nhwc_16', _p(a), _p(b), _p(c), _p(out), npix, a.shape[-1], b.shape[-1], c.shape[-1], _stream())
+  return out
+
+
 # ------------------------------------------------------------------------------------------------
 # geometry (a8-a11)
 # ------------------------------------------------------------------------------------------------
