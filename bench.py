@@ -5,14 +5,17 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 Workload (BASELINE.json configs[1]): Deep360-shape stereo-stage inference, 6 camera pairs per step, Cassini
-1024x512 (= "512x1024 equirect", SURVEY.md orientation note), maxdisp=192, bf16, out_conf=True, synthetic inputs,
-seeded random-init weights.  One step = ModeDisparity.forward on one batch of 6 pairs; the 6 pairs of a frame are
-independent, so with N GPUs every rank processes its own 6-pair batch (weak scaling) and the
-per-pair disparity/confidence maps are all-gathered (NCCL) as the fusion stage would consume them.
+1024x512 (= "512x1024 equirect", SURVEY.md orientation note), maxdisp=192, 16-bit storage (fp16: the 16-bit format that meets
+north_star's 0.01 px conv3d budget; bf16 measures 0.03 px), fp32 accumulation / logits / regression,
+out_conf=True, synthetic inputs, seeded random-init weights.  One step = ModeDisparity.forward on one batch of 6 pairs; frames
+and pairs are independent, so with N GPUs every rank processes its own frames (weak scaling, no data-path
+collective).  The all-gather of per-pair maps into the fusion stage belongs to the two-stage layout: `--mode twostage`.
 
   value  pairs/s with inputs resident in HBM, CUDA-event timed, max over ranks
   e2e    same metric through the public module API with HOST (pinned) inputs and outputs copied back to the host
-  roofline   tensor-core conv3d stack (dominant kernel family): algorithmic FLOPs / measured kernel time
+  roofline   tensor-core conv3d stack (dominant kernel family): algorithmic FLOPs / measured kernel time; `roofline.kernels` lists
+             every kernel class of the step against its BINDING bound (tensor pipe, HBM, or the MUFU exp rate)
+  reference_gpu  the UNMODIFIED reference (its Python + its own CUDA op + cuDNN/cuBLAS, staged in baseline/_ref/ref) on this GPU
   cpu_baseline  the CPU oracle (torch-CPU restatement of the reference; the reference has no CPU path of its own)
                 on a bounded sample, on this box's host cores
 
@@ -90,7 +93,11 @@ class ClockSampler(threading.Thread):
     return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
 
 
-def build_model(device, precision='bf16'):
+PRECISION = os.environ.get('MODE_B200_BENCH_PRECISION', 'fp16')  # the benchmarked 16-bit storage format
+
+
+def build_model(device, precision=None):
+  precision = precision or PRECISION
   from mode_2022_b200.models import ModeDisparity
   torch.manual_seed(0)
   m = ModeDisparity(MAXDISP, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', out_conf=True, precision=precision)
@@ -102,6 +109,142 @@ def build_model(device, precision='bf16'):
       mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) * 0.4 + 0.8)
       mod.weight.data.copy_(torch.rand(mod.weight.shape, generator=g) * 0.4 + 0.6)
   return m.to(device).eval()
+
+
+MUFU_EXP_PER_S = 148 * 16 * 1.965e9  # SFU exp2 rate: 148 SMs x 16 lanes/clk x max SM clock
+
+
+def _cval(a):
+  return a.value if hasattr(a, 'value') else a
+
+
+def roofline_report(prof, reps):
+  """Per-kernel-class roofline from CUDA-event timings of the C-ABI calls.  For every class: algorithmic FLOPs and bytes (DESIGN.md
+  section 3), the two time floors (FLOPs / sustained bf16-fp16 tensor peak, bytes / measured HBM copy bandwidth) and
+  frac = binding floor / measured time.  The top-level object is the dominant kernel family (tcgen05 conv3d), as before."""
+  pk = peaks()
+  tf_peak, hbm_peak = pk['bf16_tflops_sustained'] * 1e12, pk['hbm_gbs'] * 1e9
+  cls = {}
+
+  def add(key, ms, flops=0.0, nbytes=0.0, exps=0.0):
+    c = cls.setdefault(key, {'ms': 0.0, 'n': 0, 'flops': 0.0, 'bytes': 0.0, 'exps': 0.0})
+    c['ms'] += ms
+    c['n'] += 1
+    c['flops'] += flops
+    c['bytes'] += nbytes
+    c['exps'] += exps
+
+  for name, a, e0, e1 in prof:
+    ms = e0.elapsed_time(e1)
+    v = [_cval(x) for x in a]
+    if name == 'mode_conv3d_tc':
+      B, Ci, Co, D, Hh, Ww, mode = v[8:15]
+      vox = B * D * Hh * Ww
+      out_vox = vox if mode == 0 else (B * ((D - 1) // 2 + 1) * ((Hh - 1) // 2 + 1) * ((Ww - 1) // 2 + 1) if mode == 1 else vox * 8)
+      flops = 2.0 * 27 * Ci * Co * (out_vox if mode != 2 else vox)  # transposed conv counted over input voxels (SURVEY.md section 8d)
+      has_res = (v[4] is not None) or (v[5] is not None)
+      nbytes = vox * Ci * 2 + out_vox * Co * 2 * (2 if has_res else 1) + 27 * Ci * Co * 2
+      tag = {0: 's1', 1: 's2', 2: 'deconv'}[mode]
+      add(f'conv3d_tc {Ci}->{Co} {tag} @{D}x{Hh}x{Ww}', ms, flops, nbytes)
+    elif name == 'mode_conv3d_classifier_tc':
+      B, D, Hh, Ww = v[4:8]
+      vox = B * D * Hh * Ww
+      add(f'conv3d_cls_tc 32->1 @{D}x{Hh}x{Ww}', ms, 2.0 * 27 * 32 * vox, vox * 32 * 2 + vox * 4 * (2 if v[2] is not None else 1))
+    elif name == 'mode_sphere_conv_tc':
+      B, Cc, Hh, Ww, Co = v[7:12]
+      px = B * Hh * Ww
+      add(f'sphere_conv_tc {Cc}->{Co} @{Hh}x{Ww}', ms, 2.0 * 9 * Cc * Co * px, px * (Cc + Co * (2 if v[5] is not None else 1)) * 2 + 9 * Hh * Ww * 16 + 9 * Cc * Co * 2)
+    elif name == 'mode_costvol_conv_fused':
+      B, D4, Hh, Ww = v[5:9]
+      add('costvol_conv (cost volume + dres0[0] fused; K=96 GEMMs excluded)', ms, 0.0, 2 * B * Hh * Ww * 288 * 4 + B * D4 * Hh * Ww * 32 * 2)
+    elif name == 'mode_costvol_cols':
+      B, Hh, Ww = v[2:5]
+      add('costvol_cols', ms, 0.0, B * Hh * Ww * (32 + 96) * 2)
+    elif name == 'mode_disp_regress':
+      B, D4, H4, W4, D, Hh, Ww = v[3:10]
+      add('disp_regress (upsample + softmax + soft-argmin + confidence)', ms, 0.0, B * (D4 * H4 * W4 + 2 * Hh * Ww) * 4, exps=float(B) * D * Hh * Ww)
+    elif name == 'mode_stem_conv_tc':
+      B0, B1, Hh, Ww = v[6:10]
+      px_o = (B0 + B1) * ((Hh - 1) // 2 + 1) * ((Ww - 1) // 2 + 1)
+      add('stem_conv_tc 3->32 7x7 s2', ms, 2.0 * 147 * 32 * px_o, (B0 + B1) * 3 * Hh * Ww * 4 + px_o * 32 * 2)
+    elif name == 'mode_concat3_nhwc_16':
+      npix, ca, cb, cc = v[4:8]
+      add('concat3_nhwc', ms, 0.0, 2 * npix * (ca + cb + cc) * 2)
+    else:
+      add(name, ms)
+  kernels = []
+  for key, c in cls.items():
+    t = c['ms'] / reps * 1e-3
+    fl, by, ex = c['flops'] / reps, c['bytes'] / reps, c['exps'] / reps
+    floors = {'tensor': fl / tf_peak, 'hbm': by / hbm_peak}
+    if ex:
+      floors['mufu_exp'] = ex / MUFU_EXP_PER_S
+    bound = max(floors, key=floors.get)
+    ent = {'kernel': key, 'launches_per_step': c['n'] // reps, 'ms_per_step': round(t * 1e3, 4), 'bound': bound, 'frac': round(floors[bound] / t, 3) if t > 0 else None}
+    if fl:
+      ent['TFLOPs'] = round(fl / t / 1e12, 1)
+      ent['frac_tensor'] = round(floors['tensor'] / t, 3)
+    if by:
+      ent['GBps'] = round(by / t / 1e9, 1)
+      ent['frac_hbm'] = round(floors['hbm'] / t, 3)
+    if ex:
+      ent['Texp_per_s'] = round(ex / t / 1e12, 3)
+    kernels.append(ent)
+  kernels.sort(key=lambda e: -e['ms_per_step'])
+  conv = [c for k, c in cls.items() if k.startswith('conv3d_')]
+  t_conv = sum(c['ms'] for c in conv) / reps
+  fl_conv = sum(c['flops'] for c in conv) / reps
+  ach = fl_conv / (t_conv * 1e-3) / 1e12 if t_conv > 0 else 0.0
+  n_conv = sum(c['n'] for c in conv) // reps
+  fused_first = any(k.startswith('costvol_conv') for k in cls)
+  return {'bound': 'tensor',
+          'kernel': f'conv3d_tc_kernel + conv3d_cls_tc_kernel ({n_conv} conv3d/deconv3d/classifier launches per step' + ('; the first layer of the 3-D stack is fused with the cost volume)' if fused_first else ')'),
+          'achieved': round(ach, 1), 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['bf16_tflops_sustained'], 3),
+          'traffic': CONV3D_DRAM_BYTES_PER_STEP,
+          'traffic_note': 'DRAM read+write bytes of the conv3d launches of one step (6 pairs), ncu launch list under profiles/',
+          'peak_source': pk['source'] + ' (sustained 16-bit dense; burst %.0f; HBM %.1f GB/s; MUFU exp %.2f T/s nominal)' % (pk['bf16_tflops'], pk['hbm_gbs'], MUFU_EXP_PER_S / 1e12),
+          'launches_per_step': n_conv, 'ms_per_step_in_kernel': round(t_conv, 3),
+          'kernels': kernels}
+
+
+def reference_gpu_block(dev):
+  """The UNMODIFIED reference on this GPU ('that, not the CPU, is the number to beat'): its own Python, its own
+  compiled CUDA op and cuDNN/cuBLAS with torch's default settings, from baseline/_ref/ref (oracle/stage_reference.py).  A bounded
+  sample: 1 pair per forward, device-resident inputs (the reference's host-side cost-volume upload is inside its forward)."""
+  try:
+    from oracle import mode_oracle as O
+    from oracle import stage_reference as SR
+    from tests.helpers import KEY_SHAPES
+    pkg = SR.reference_package()
+    if pkg is None:
+      return {'unavailable': 'baseline/_ref/ref is not staged on this box (python oracle/stage_reference.py)'}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False  # torch defaults = what a reference user gets
+    m = pkg.ModeDisparity(MAXDISP, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', out_conf=True)
+    m.load_state_dict(O.synthetic_state_dict(KEY_SHAPES, seed=0))
+    m = m.to(dev).eval()
+    g = torch.Generator().manual_seed(0)
+    l, r = torch.randn(1, 3, H, W, generator=g).to(dev), torch.randn(1, 3, H, W, generator=g).to(dev)
+    with torch.no_grad():
+      for _ in range(2):
+        m(l, r)
+      torch.cuda.synchronize()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      n = 4
+      a.record()
+      for _ in range(n):
+        m(l, r)
+      b.record()
+      torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    del m
+    torch.cuda.empty_cache()
+    return {'value': round(1e3 / ms, 2), 'unit': 'pairs/s', 'ms_per_pair': round(ms, 2), 'n_gpus': 1,
+            'sample': f'{n} forwards of 1 pair 1024x512 D=192, fp32 NCHW, cuDNN TF32 allowed (torch default), matmul fp32 (torch default), eval, out_conf',
+            'impl': 'unmodified reference ModeDisparity + its compiled sphere_conv_cuda extension (baseline/_ref/ref)'}
+  except Exception as e:  # the checker must never take the bench down
+    return {'unavailable': f'{type(e).__name__}: {e}'[:300]}
 
 
 def run_ours(args):
@@ -118,11 +261,10 @@ def run_ours(args):
   left_h = torch.randn(PAIRS, 3, H, W, generator=g).pin_memory()
   right_h = torch.randn(PAIRS, 3, H, W, generator=g).pin_memory()
   left, right = left_h.to(dev), right_h.to(dev)
-  gather = [torch.empty(2, PAIRS, 1, H, W, device=dev) for _ in range(world)] if world > 1 else None
 
   def exchange(pred, conf):
-    if world > 1:  # per-pair disparity/confidence maps to the fusion stage
-      dist.all_gather(gather, torch.stack([pred, conf]))
+    """Default mode: frames are independent and every rank owns whole frames, so the hot path has no exchange step (the
+    all-gather into the fusion stage is measured by --mode twostage, where the 6 pairs of ONE frame are sharded)."""
 
   # ---- device-resident step, captured in a CUDA graph (static shapes; ~250 launches per step)
   with torch.no_grad():
@@ -210,39 +352,24 @@ def run_ours(args):
     ms_e2e = e2e_run(args.steps)
     pred_h, conf_h = pipe.h_pred[0], pipe.h_conf[0]
 
-    # ---- roofline of the dominant kernel family (tcgen05 conv3d): CUDA events around every C-ABI call, eager pass
-    roof = None
+    # ---- roofline: CUDA events around every C-ABI call of an eager pass (the graph replays the same kernels)
+    roof, ref_gpu = None, None
     if rank == 0:
       _lib.PROFILE = []
       for _ in range(3):
         model(left, right)
       torch.cuda.synchronize()
       prof, _lib.PROFILE = _lib.PROFILE, None
-      by = {}
-      for name, _a, e0, e1 in prof:
-        by.setdefault(name, []).append(e0.elapsed_time(e1))
-      conv_names = ('mode_conv3d_tc', 'mode_conv3d_classifier_tc')  # the 28 conv3d/deconv3d layers of the stack
-      t_conv = sum(sum(by.get(k, [])) for k in conv_names) / 3.0  # ms per step in the conv3d kernels
-      n_conv = sum(len(by.get(k, [])) for k in conv_names) // 3
-      pk = peaks()
-      # dres0[0] (64 -> 32 on the cost volume, 2*27*64*32*48*256*128 = 173.9 GFLOP / pair) does not run as a conv3d kernel when it is
-      # fused with the cost volume (costvol_conv.cu: two small GEMMs + a write-bound kernel): its FLOPs leave the numerator too
-      fused_first = 'mode_costvol_conv_fused' in by
-      flops = (CONV3D_GFLOP_PER_PAIR - (173.9 if fused_first else 0.0)) * 1e9 * PAIRS
-      ach = flops / (t_conv * 1e-3) / 1e12 if t_conv > 0 else 0.0
-      roof = {'bound': 'tensor', 'kernel': 'conv3d_tc_kernel + conv3d_cls_tc_kernel (24 conv3d/deconv3d launches per step + 3 classifier launches; the first layer of the 3-D stack is fused with the cost volume)' if fused_first else 'conv3d_tc_kernel + conv3d_cls_tc_kernel (28 layers of the 3-D stack)', 'achieved': round(ach, 1),
-              'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['bf16_tflops_sustained'], 3), 'traffic': CONV3D_DRAM_BYTES_PER_STEP,
-              'traffic_note': 'DRAM read+write bytes of the 27 conv3d launches of one step (6 pairs), ncu launch list profiles/r01_launch_list_summary.md',
-              'peak_source': pk['source'] + ' (sustained bf16; burst %.0f)' % pk['bf16_tflops'], 'launches_per_step': n_conv,
-              'ms_per_step_in_kernel': round(t_conv, 3),
-              'other_kernels_ms_per_step': {k: round(sum(v) / 3.0, 3) for k, v in by.items() if k not in conv_names}}
+      roof = roofline_report(prof, 3)
+      if world == 1:
+        ref_gpu = reference_gpu_block(dev)
 
   pairs = PAIRS * world * args.steps
   out = {
       'metric': 'stereo pairs/s @512x1024 D=192', 'value': round(pairs / (ms * 1e-3), 2), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
       'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-      'dtype': 'bf16', 'data': 'synthetic (randn images, seeded random-init weights)',
-      'config': {'workload': WORKLOAD, 'pairs_per_step_per_gpu': PAIRS, 'parallelism': f'pairs sharded over {world} GPU(s), no data-path collective; all-gather of disp/conf maps',
+      'dtype': PRECISION, 'data': 'synthetic (randn images, seeded random-init weights)',
+      'config': {'workload': WORKLOAD, 'pairs_per_step_per_gpu': PAIRS, 'parallelism': f'frames (6 pairs each) sharded over {world} GPU(s), weights replicated, no data-path collective',
                  'l2': 'per-step working set (>2 GB of activations) exceeds the 126 MB L2', 'cuda_graph': graph is not None},
       'e2e': {'value': round(pairs / (ms_e2e * 1e-3), 2), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(left_h.numel() * 4 * 2), 'd2h_bytes_per_step': int(pred_h.numel() * 4 * 2),
               'ms_per_step': round(ms_e2e / args.steps, 3),
@@ -252,6 +379,8 @@ def run_ours(args):
   }
   if rank == 0:
     out['roofline'] = roof
+    if ref_gpu is not None:
+      out['reference_gpu'] = ref_gpu
     out['cpu_baseline'] = cpu_baseline(sample_only=True)
     print(json.dumps(out), flush=True)
   if world > 1:

@@ -50,6 +50,14 @@ constexpr int kNumSMs = 148;  // B200
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute is per device: launchers keep their high-water marks per (thread, device)
+constexpr int kMaxDevices = 64;
+static inline int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < kMaxDevices) ? d : 0;
+}
+
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 __device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
   __nv_bfloat16 h = __float2bfloat16_rn(f);
@@ -75,8 +83,10 @@ __device__ __forceinline__ void unpack2(uint32_t v, float& lo, float& hi) {
 template <int FMT>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   if (FMT == kFmtBF16) return pack_bf16x2(lo, hi);
-  const __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  // fp16 storage saturates instead of overflowing to inf (|x| > 65504 -> +-65504; NaN stays NaN): one F2FP.SATFINITE, same cost
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ uint16_t float_to_h16_bits(float f, int fmt) {
   if (fmt == kFmtBF16) return float_to_bf16_bits(f);

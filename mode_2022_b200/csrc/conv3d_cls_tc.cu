@@ -322,7 +322,8 @@ extern "C" int mode_conv3d_classifier_tc(const mode_h16* x, const float* w, cons
   p.chunk = best_chunk, p.nchunks = ceil_div(D, best_chunk);
   p.nitems = cols * p.nchunks;
   const size_t smem = 1024 + (size_t)kSlots * kSlotBytes + 2048 + (size_t)3 * kTPlane * 4 + (2 * kSlots + 2 * kTmemRing + 6) * 8 + 16;
-  static thread_local bool attr = false;
+  static thread_local bool attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  bool& attr = attr_dev[current_device()];
   if (!attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_cls_tc_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_classifier_tc");
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_cls_tc_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_classifier_tc");

@@ -141,7 +141,8 @@ extern "C" int mode_conv3d_f32(const float* x, const float* w, const float* scal
   const int groups = ceil_div(Co, kCoT);
   const int by = std::min(groups, 8);
   const size_t smem = (size_t)kCi3 * 27 * by * kCoT * sizeof(float);
-  static thread_local size_t attr = 0;
+  static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
   if (smem > 48 * 1024 && smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_f32");
     attr = smem;

@@ -902,7 +902,8 @@ int make_tmap_res(CUtensorMap* tm, const void* ptr, int fmt, int Co, int Wo, int
 
 template <int MODE, int NT, int FMT, int SC>
 int launch_tc3(const TcParams& p, const CUtensorMap& tm, const CUtensorMap& tmr, int grid, size_t smem, cudaStream_t s) {
-  static thread_local size_t attr = 0;
+  static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
   if (smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<MODE, NT, FMT, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "conv3d_tc");
     attr = smem;

@@ -173,7 +173,8 @@ extern "C" int mode_costvol_conv_fused(const float* ur, const float* ut, const f
   MODE_CHECK_ARG(B > 0 && D4 > 0 && H > 0 && W > 0, "costvol_conv_fused: bad shape");
   const size_t smem = (size_t)2 * W * 32 * sizeof(float);
   MODE_CHECK_ARG(smem <= 200 * 1024, "costvol_conv_fused: feature map too wide (W = %d)", W);
-  static thread_local size_t attr = 0;
+  static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
   if (smem > 48 * 1024 && smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(costvol_conv_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "costvol_conv_fused");
     MODE_CHECK_CUDA(cudaFuncSetAttribute(costvol_conv_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "costvol_conv_fused");

@@ -104,7 +104,8 @@ extern "C" int mode_disp_regress(const float* cost, float* pred, float* conf, in
   MODE_CHECK_ARG(D4 <= 128, "disp_regress: D/4 = %d > 128 not supported", D4);
   const float sd = (float)(D4 - 1) / (float)(D - 1), sh = (float)(H4 - 1) / (float)(H - 1), sw = (float)(W4 - 1) / (float)(W - 1);
   const size_t smem = (size_t)D4 * kRegThreads * sizeof(float);
-  static thread_local int attr_set_for = 0;
+  static thread_local int attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  int& attr_set_for = attr_dev[current_device()];
   if (smem > 48 * 1024 && attr_set_for < (int)smem) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(disp_regress_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "disp_regress");
     MODE_CHECK_CUDA(cudaFuncSetAttribute(disp_regress_kernel<48, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "disp_regress");

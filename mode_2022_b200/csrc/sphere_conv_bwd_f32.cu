@@ -196,7 +196,8 @@ extern "C" int mode_sphere_conv_backward_f32(const float* x, const float* pos, c
     const int by = std::min(groups, 4);
     const size_t smem = (size_t)Co * by * kCPerThread * sizeof(float);
     MODE_CHECK_ARG(smem <= 200 * 1024, "sphere_conv_backward_f32: Co = %d too large", Co);
-    static thread_local size_t attr = 0;
+    static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
     if (smem > 48 * 1024 && smem > attr) {
       MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_dgrad_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_backward_f32");
       attr = smem;

@@ -106,7 +106,8 @@ extern "C" int mode_sphere_conv_f32(const float* x, const float* pos, const floa
   const int CoBlk = by * kCoPerThread;
   const size_t smem = (size_t)kCiChunk * KK * CoBlk * sizeof(float);
   MODE_CHECK_ARG(smem <= 200 * 1024, "sphere_conv_f32: kernel %dx%d too large", Kh, Kw);
-  static thread_local size_t attr = 0;
+  static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
   if (smem > 48 * 1024 && smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_f32");
     attr = smem;

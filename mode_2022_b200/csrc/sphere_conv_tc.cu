@@ -18,6 +18,7 @@
 // 1.18 MB of L1 traffic (~9.2k wavefront cycles) against 4.6k MMA cycles.  One CTA (16 gather warps) per SM with a
 // minimal shared-memory carve-out, so that the tile's ~45 KB input neighbourhood stays L1 resident across the 36 re-reads.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -31,20 +32,22 @@ constexpr int kStagesS = 3;
 constexpr int kChunkStrideA = 128 * 16 + 16;             // 2064 B: +16 B pad -> conflict-free STS.128 from 8 chunk-lanes
 constexpr int kABytes = ((8 * kChunkStrideA) + 127) & ~127;  // 16640
 
-// packed 16-bit blend: r = w1*v1 + w2*v2 + w3*v3 + w4*v4 on two channels at once (HFMA2.BF16 / HFMA2): 4 instructions per
-// channel pair instead of 2 unpacks + 8 FFMAs + a pack; the price is that the partial sums are rounded to the storage
-// format.  w12 = (w1, w2), w34 = (w3, w4) as 16-bit pairs: the broadcasts fold into HFMA2 operand selectors (.H0_H0 / .H1_H1).
+// Bilinear blend r = w1*v1 + w2*v2 + w3*v3 + w4*v4 of two channels.  The weights live in the gather table as fp16 pairs
+// w12 = (w1, w2), w34 = (w3, w4) for BOTH storage formats (weights are in [0, 1]: fp16 keeps 11 bits of them).
+//   fp16 storage: packed HFMA2 (the broadcasts fold into operand selectors .H0_H0 / .H1_H1); the three partial sums are rounded
+//                 to fp16 (2^-12 each -- together still below ONE bf16 rounding);
+//   bf16 storage: unpack, four fp32 FMAs per channel in the reference's expression order (kernel.cu:111), ONE rounding.
 template <int FMT>
 __device__ __forceinline__ uint32_t blend2(uint32_t w12, uint32_t w34, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t v4) {
+  const __half2 a = *reinterpret_cast<__half2*>(&w12), b = *reinterpret_cast<__half2*>(&w34);
   if (FMT == kFmtBF16) {
-    const __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&w12), b = *reinterpret_cast<__nv_bfloat162*>(&w34);
-    const __nv_bfloat162 r = __hfma2(__high2bfloat162(b), *reinterpret_cast<__nv_bfloat162*>(&v4),
-                             __hfma2(__low2bfloat162(b), *reinterpret_cast<__nv_bfloat162*>(&v3),
-                             __hfma2(__high2bfloat162(a), *reinterpret_cast<__nv_bfloat162*>(&v2),
-                             __hmul2(__low2bfloat162(a), *reinterpret_cast<__nv_bfloat162*>(&v1)))));
-    return *reinterpret_cast<const uint32_t*>(&r);
+    const float2 wa = __half22float2(a), wb = __half22float2(b);
+    float l1, h1, l2, h2, l3, h3, l4, h4;
+    unpack2<kFmtBF16>(v1, l1, h1), unpack2<kFmtBF16>(v2, l2, h2), unpack2<kFmtBF16>(v3, l3, h3), unpack2<kFmtBF16>(v4, l4, h4);
+    const float lo = fmaf(wb.y, l4, fmaf(wb.x, l3, fmaf(wa.y, l2, wa.x * l1)));
+    const float hi = fmaf(wb.y, h4, fmaf(wb.x, h3, fmaf(wa.y, h2, wa.x * h1)));
+    return pack_bf16x2(lo, hi);
   } else {
-    const __half2 a = *reinterpret_cast<__half2*>(&w12), b = *reinterpret_cast<__half2*>(&w34);
     const __half2 r = __hfma2(__high2half2(b), *reinterpret_cast<__half2*>(&v4),
                       __hfma2(__low2half2(b), *reinterpret_cast<__half2*>(&v3),
                       __hfma2(__high2half2(a), *reinterpret_cast<__half2*>(&v2),
@@ -73,6 +76,9 @@ struct ScParams {
   int ntiles;
   int tw, th, tiles_x, tiles_y;  // tile = th x tw pixels (th*tw == 128); tw == 0: linear tiles of 128 consecutive pixels
   int epi_tma;                   // epilogue moves the residual / output tiles with TMA (2-D tiles, Co/ngrp == 32)
+  // list mode (the slab kernel below takes every tile whose neighbourhood fits its shared-memory slab; this kernel the rest):
+  const int* plist;              // tile positions (ty*tiles_x + tx) this launch processes in every image, or null = all tiles
+  const int* pcount;             // device-side length of plist
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,6 +145,12 @@ __device__ __forceinline__ long long tile_pixel(const ScParams& p, int tile, int
   const int y = ty * p.th + r / p.tw, x = tx * p.tw + r % p.tw;
   return (long long)b * HW + (long long)y * p.W + x;
 }
+// list mode: item i of this launch -> tile id (b * tiles per image + listed position)
+__device__ __forceinline__ int tile_of_item(const ScParams& p, int i, int nlist) {
+  if (p.plist == nullptr) return i;
+  const int b = i / nlist;
+  return b * (p.tiles_x * p.tiles_y) + __ldg(p.plist + (i - b * nlist));
+}
 
 // CC: compile-time channel count (128 = the model's layer4; 0 = read it from the parameters)
 template <int FMT, int CC>
@@ -184,8 +196,10 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
   const int nhalf = C / 64;
   const int nstage_tile = 9 * nhalf;
   // contiguous tile ranges per CTA: consecutive tiles are consecutive image rows and share 2 of their 3 input rows in L1
-  const int tiles_per = (p.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int tile0 = (int)blockIdx.x * tiles_per, tile1 = min(tile0 + tiles_per, p.ntiles);
+  const int nlist = p.pcount ? __ldg(p.pcount) : 0;
+  const int nitems = p.plist ? p.B * nlist : p.ntiles;
+  const int tiles_per = (nitems + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile0 = min((int)blockIdx.x * tiles_per, nitems), tile1 = min(tile0 + tiles_per, nitems);  // ITEM range of this CTA
 
   if (warp < kGatherWarps) {
     // =================================================== gather producers (+ epilogue)
@@ -200,7 +214,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
       const int per_img = p.tiles_x * p.tiles_y;
       const int b = tile / per_img, t = tile - b * per_img;
       const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
-      cx = tx * 16, cy = b * p.H + ty * 8 + 2 * q;
+      cx = tx * p.tw, cy = b * p.H + ty * p.th + (32 / p.tw) * q;
     };
     // ---- epilogue of one tile: warp w reads TMEM lanes 32*(w%4).., column group w/4 of ngrp (4 groups when Co % 128 == 0,
     // else 2).  It runs one stage into the NEXT tile's gather (the accumulator is double buffered), so the tensor pipe's
@@ -208,7 +222,8 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
     // With 2-D tiles the residual piece arrives by TMA and the output piece leaves by TMA through a 64-byte-swizzled 2 KB
     // tile per warp: row-per-thread global accesses (16 B at a 256 B stride = 32 L1 wavefronts per instruction) would
     // spend a fifth of the L1 data pipe -- the kernel's bound -- on the epilogue.
-    auto epilogue = [&](int tile, uint32_t tn) {
+    auto epilogue = [&](int item, uint32_t tn) {
+      const int tile = tile_of_item(p, item, nlist);
       const uint32_t buf = tn & 1;
       mbar_wait(smem_u32(tfull_bar + buf), (tn >> 1) & 1);
       tc_fence_after();
@@ -276,7 +291,8 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
     uint4 v1[2], v2[2], v3[2], v4[2];  // corner values; loop carried so that skipped loads leave finite data behind
 #pragma unroll
     for (int j = 0; j < 2; ++j) v1[j] = v2[j] = v3[j] = v4[j] = make_uint4(0, 0, 0, 0);
-    for (int tile = tile0; tile < tile1; ++tile, ++tile_n) {
+    for (int item = tile0; item < tile1; ++item, ++tile_n) {
+      const int tile = tile_of_item(p, item, nlist);
       // this thread's two pixels of the tile: table row (pixel inside the image) and batch offset (b*HW)
       int pp[2];
       uint32_t base[2];
@@ -296,7 +312,7 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
       const uint32_t wmask0 = pp[0] >= 0 ? 0xffffffffu : 0u, wmask1 = pp[1] >= 0 ? 0xffffffffu : 0u;
       const ptrdiff_t rowC = (ptrdiff_t)p.W * C;
       for (int s = 0; s < nstage_tile; ++s, ++stage) {
-        if (s == 1 && tile > tile0) epilogue(tile - 1, tile_n - 1);
+        if (s == 1 && item > tile0) epilogue(item - 1, tile_n - 1);
         if (s == 4 && p.epi_tma && p.res != nullptr && grp < ngrp && lane == 0) {
           // this tile's residual piece -> the warp's epilogue tile (free once the previous tile's output store has read it)
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -401,32 +417,99 @@ __global__ void __launch_bounds__(kThreadsS, 1) sphere_conv_tc_kernel(const ScPa
   if (warp == kGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
-// gather table: for every (tap, pixel) the top-left corner's pixel index (the other three are +1, +W, +W+1) and the four
-// bilinear weights rounded to the layer's 16-bit storage format, with the reference's rules folded in (kernel.cu:246 tap
-// guard, :97-107 per-corner guards -> weight 0, :109 weights).  A corner of weight 0 is never fetched, so its index may
-// point outside the image.  16 bytes per entry; depends only on the sampling grid and the format.
-__global__ void sphere_table_kernel(const float* __restrict__ pos, int4* __restrict__ table, int H, int W, int KK, int fmt) {
+// gather table: for every (tap, pixel) the top-left corner's pixel index (the other three are +1, +W, +W+1), the four
+// bilinear weights as fp16 (both storage formats blend with them, see blend2), with the reference's rules folded in
+// (kernel.cu:246 tap guard, :97-107 per-corner guards -> weight 0, :109 weights), and the corner's (row, col) packed as two
+// int16 for the slab kernel.  A corner of weight 0 is never fetched, so its index may point outside the image.  16 bytes per
+// entry; depends only on the sampling grid.
+__global__ void sphere_table_kernel(const float* __restrict__ pos, int4* __restrict__ table, int H, int W, int KK) {
   const int HW = H * W;
   const long long n = (long long)KK * HW;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(e / HW), pp = (int)(e - (long long)k * HW);
     const float h_im = pos[(size_t)(2 * k) * HW + pp], w_im = pos[(size_t)(2 * k + 1) * HW + pp];
-    int idx = 0;
+    int idx = 0, hl = pp / W, wl = pp - (pp / W) * W;  // dropped tap: all weights 0, corner = the pixel itself
     float4 wt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (h_im > -1 && w_im > -1 && h_im < H && w_im < W) {
       const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
       const int h_high = h_low + 1, w_high = w_low + 1;
       const float lh = h_im - h_low, lw = w_im - w_low, hh = 1 - lh, hw = 1 - lw;
-      idx = h_low * W + w_low;
+      idx = h_low * W + w_low, hl = h_low, wl = w_low;
       if (h_low >= 0 && w_low >= 0) wt.x = hh * hw;
       if (h_low >= 0 && w_high <= W - 1) wt.y = hh * lw;
       if (h_high <= H - 1 && w_low >= 0) wt.z = lh * hw;
       if (h_high <= H - 1 && w_high <= W - 1) wt.w = lh * lw;
     }
-    const uint32_t w12 = (uint32_t)float_to_h16_bits(wt.x, fmt) | ((uint32_t)float_to_h16_bits(wt.y, fmt) << 16);
-    const uint32_t w34 = (uint32_t)float_to_h16_bits(wt.z, fmt) | ((uint32_t)float_to_h16_bits(wt.w, fmt) << 16);
-    table[e] = make_int4(idx, (int)w12, (int)w34, 0);
+    const uint32_t w12 = (uint32_t)float_to_h16_bits(wt.x, kFmtFP16) | ((uint32_t)float_to_h16_bits(wt.y, kFmtFP16) << 16);
+    const uint32_t w34 = (uint32_t)float_to_h16_bits(wt.z, kFmtFP16) | ((uint32_t)float_to_h16_bits(wt.w, kFmtFP16) << 16);
+    table[e] = make_int4(idx, (int)w12, (int)w34, (int)(((uint32_t)hl << 16) | ((uint32_t)wl & 0xffffu)));
   }
+}
+
+// ---- tile classes -------------------------------------------------------------------------------------------------------
+// The slab kernel stages the input neighbourhood of a 128-pixel tile in shared memory.  Per tile position (the same for every
+// image) this kernel measures that neighbourhood from the gather table: along the LONG image axis (longitude: rows of a Cassini
+// map, columns of an ERP map -- the axis the sampling grid wraps around and along which the footprint grows like 1/cos(lat))
+// the first line l0 and the line count L, modulo the axis length; along the short axis the first pixel s0 of a kSlabShort window.
+// Tiles with L <= kSlabLines whose short extent fits go to the slab kernel ("fast"), the rest (the polar tile columns, where
+// one tap reaches half-way round the sphere) to the direct-gather kernel above.
+constexpr int kSlabShort = 12;                        // tile short side 8 + 2 + 2: taps reach [-2, +2] columns (rows for ERP)
+constexpr int kSlabLineBytes = kSlabShort * 128;      // one line of the slab: 12 pixels x 64 channels x 2 B
+constexpr int kSlabLines = 32;                        // 16 + 2 * 8: footprints up to +-7.5 lines
+constexpr int kSlabBytes = kSlabLines * kSlabLineBytes;  // 49152 per (tile, channel half), 1024-aligned
+
+__global__ void sphere_tileinfo_kernel(const int4* __restrict__ table, int4* __restrict__ info, int H, int W, int KK, int TH, int TW) {
+  __shared__ int s_min_l, s_max_l, s_min_s, s_max_s, s_bad;
+  const int tiles_x = W / TW;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const bool cassini = TH > TW;  // long axis = rows
+  const int LEN = cassini ? H : W, tl0 = cassini ? ty * TH : tx * TW;
+  if (threadIdx.x == 0) s_min_l = 1 << 30, s_max_l = -(1 << 30), s_min_s = 1 << 30, s_max_s = -(1 << 30), s_bad = 0;
+  __syncthreads();
+  const int m = threadIdx.x, h = ty * TH + m / TW, w = tx * TW + m % TW;
+  int min_l = 1 << 30, max_l = -(1 << 30), min_s = 1 << 30, max_s = -(1 << 30), bad = 0;
+  for (int k = 0; k < KK; ++k) {
+    const int4 e = table[(size_t)k * H * W + (size_t)h * W + w];
+    const uint32_t wb[4] = {(uint32_t)e.y & 0xffffu, (uint32_t)e.y >> 16, (uint32_t)e.z & 0xffffu, (uint32_t)e.z >> 16};
+    if ((wb[0] | wb[1] | wb[2] | wb[3]) == 0) continue;  // dropped tap: nothing is fetched
+    const int hl = e.w >> 16, wl = (int)(short)(e.w & 0xffff);
+    if (hl < 0 || wl < 0) bad = 1;  // top-left corner outside the image: the slab address arithmetic assumes it is inside
+    for (int c = 0; c < 4; ++c) {
+      if (c != 0 && wb[c] == 0) continue;  // the top-left corner anchors the address arithmetic: always inside the slab
+      const int ch = hl + (c >> 1), cw = wl + (c & 1);
+      const int lng = cassini ? ch : cw, sht = cassini ? cw : ch;
+      int dl = (lng - tl0 + LEN / 2) % LEN;  // signed offset from the tile's first line, wrapped into [-LEN/2, LEN/2)
+      if (dl < 0) dl += LEN;
+      dl -= LEN / 2;
+      min_l = min(min_l, dl), max_l = max(max_l, dl), min_s = min(min_s, sht), max_s = max(max_s, sht);
+    }
+  }
+  atomicMin(&s_min_l, min_l), atomicMax(&s_max_l, max_l), atomicMin(&s_min_s, min_s), atomicMax(&s_max_s, max_s);
+  if (bad) atomicOr(&s_bad, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int4 r = make_int4(0, 0, 0, (ty << 16) | tx);  // z = 0: not a slab tile
+    if (s_max_l < s_min_l) {
+      r.z = 1;  // no tap at all in this tile: one (unused) line
+    } else if (!s_bad && s_max_l - s_min_l + 1 <= kSlabLines && s_max_s - s_min_s + 1 <= kSlabShort) {
+      int l0 = (tl0 + s_min_l) % LEN;
+      if (l0 < 0) l0 += LEN;
+      r.x = l0, r.y = s_min_s, r.z = s_max_l - s_min_l + 1;
+    }
+    info[blockIdx.x] = r;
+  }
+}
+// header {n_fast, n_rest, TH, TW} + the two position lists (deterministic order)
+__global__ void sphere_tilelist_kernel(const int4* __restrict__ info, int* __restrict__ hdr, int* __restrict__ fast, int* __restrict__ rest, int npos, int TH, int TW) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int nf = 0, nr = 0;
+  for (int i = 0; i < npos; ++i) {
+    if (info[i].z > 0)
+      fast[nf++] = i;
+    else
+      rest[nr++] = i;
+  }
+  hdr[0] = nf, hdr[1] = nr, hdr[2] = TH, hdr[3] = TW;
 }
 
 // (Co, C, 3, 3) fp32 -> [tap 9][half C/64][chunk 8][n Co][8] bf16
@@ -446,20 +529,27 @@ __global__ void pack_wsphere_kernel(const float* __restrict__ w, uint16_t* __res
   }
 }
 
-int make_epi_tmap(CUtensorMap* tm, const void* ptr, int fmt, int Co, int W, long long rows) {
+decltype(&cuTensorMapEncodeTiled) tmap_encoder() {
   static decltype(&cuTensorMapEncodeTiled) encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult qres;
     void* fn = nullptr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
       set_error("sphere_conv_tc: cuTensorMapEncodeTiled is not available from this driver");
-      return MODE_ECUDA;
+      return nullptr;
     }
     encode = reinterpret_cast<decltype(&cuTensorMapEncodeTiled)>(fn);
   }
+  return encode;
+}
+
+// epilogue tiles: (Co, W, B*H) view of an NHWC tensor, box 32 channels x tw columns x 32/tw rows (one warp's 32 pixels), 64-byte swizzle
+int make_epi_tmap(CUtensorMap* tm, const void* ptr, int fmt, int Co, int W, long long rows, int tw) {
+  auto encode = tmap_encoder();
+  if (!encode) return MODE_ECUDA;
   const cuuint64_t gdim[3] = {(cuuint64_t)Co, (cuuint64_t)W, (cuuint64_t)rows};
   const cuuint64_t gstr[2] = {(cuuint64_t)Co * 2, (cuuint64_t)W * Co * 2};
-  const cuuint32_t box[3] = {32, 16, 2}, estr[3] = {1, 1, 1};
+  const cuuint32_t box[3] = {32, (cuuint32_t)tw, (cuuint32_t)(32 / tw)}, estr[3] = {1, 1, 1};
   const CUresult r = encode(tm, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -467,6 +557,351 @@ int make_epi_tmap(CUtensorMap* tm, const void* ptr, int fmt, int Co, int W, long
     return MODE_ECUDA;
   }
   return MODE_OK;
+}
+
+// slab lines: (C, W, H, B) view of the NHWC input, box = 64 channels x kSlabShort pixels along the SHORT image axis x one line of
+// the long axis, 128-byte swizzle, zero fill outside the image (= the reference's zero corners, kernel.cu:97-107)
+int make_slab_tmap(CUtensorMap* tm, const void* ptr, int fmt, int B, int C, int H, int W, bool cassini) {
+  auto encode = tmap_encoder();
+  if (!encode) return MODE_ECUDA;
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, cassini ? (cuuint32_t)kSlabShort : 1u, cassini ? 1u : (cuuint32_t)kSlabShort, 1}, estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(tm, fmt == kFmtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("sphere_conv_tc: cuTensorMapEncodeTiled (slab) failed (CUresult %d)", (int)r);
+    return MODE_ECUDA;
+  }
+  return MODE_OK;
+}
+
+// =============================================================================================================================
+// Slab kernel: the gather reads SHARED memory and the A operand lives in TENSOR memory.
+//
+// The direct-gather kernel above spends its time in the L1 pipe and in instruction issue: per 128-pixel tile it issues 65 k warp
+// instructions (225 per warp and stage: 64-bit address arithmetic, a table entry per 8-channel chunk, predicates) and its 36 corner
+// loads per pixel are L1/L2 round trips (ncu r01: issue 52 %, L1 data pipe 57 %, long-scoreboard stalls, tensor pipe 10 %).  Here:
+//   * a loader thread stages the tile's input neighbourhood (<= 32 lines x 12 pixels x 64 channels, 128-byte-swizzled) in shared
+//     memory with one TMA box per line of the long (wrapping) image axis -- the longitude wrap of the sampling grid is a different
+//     line coordinate, out-of-image pixels are TMA zero fill;
+//   * gather threads own one PIXEL each (= one TMEM lane) and 16 channels: one table entry per (pixel, tap), 8 conflict-free
+//     LDS.128 (corner x chunk; zero-weight corners predicated off), the blend, and ONE tcgen05.st of the 16 blended channels
+//     straight into the A operand in tensor memory -- no A tile in shared memory, so the 128 B/clk shared-memory port carries only
+//     the corner loads, the weight slabs (B operand) and their TMA fills;
+//   * tcgen05.mma reads A from TMEM (.kind::f16 "TS" form), B from the shared-memory ring; accumulators double-buffered in TMEM.
+// Tiles whose neighbourhood does not fit (polar tile columns: a tap reaches +-128 lines) are left to the direct-gather kernel.
+// =============================================================================================================================
+constexpr int kFStages = 5;                              // ring depth: A slots in TMEM (32 columns each) and weight slabs in smem
+constexpr int kFThreads = (kGatherWarps + 3) * 32;       // 16 gather/epilogue warps, MMA warp, weight loader, slab loader
+constexpr int kFBBytes = 128 * 64 * 2;                   // one weight slab: Co = 128 x 64 channels
+constexpr int kSlabPitch = 13;                           // pixels per slab line (12 loaded + 1 pad): odd, so that steps of one LINE also
+                                                         // walk all eight 16-byte positions of the 128-byte swizzle (ERP lanes)
+constexpr int kSlabPitchBytes = kSlabPitch * 128;
+constexpr int kSlabBufBytes = ((kSlabLines * kSlabPitchBytes) + 1023) & ~1023;  // 53248
+constexpr int kTmemAcc = 256;                            // two 128-column accumulators, then the A ring
+
+struct FcParams {
+  const int4* table;    // [9][H*W] gather entries
+  const int* hdr;       // {n_fast, n_rest, TH, TW}, then int4 info[npos], then the fast / rest position lists
+  const uint16_t* wpk;  // [9][C/64][8][128][8]
+  const float* scale;
+  const float* shift;
+  int has_res, relu;
+  int B, C, H, W, npos;
+  int th, tw, tw_shift, cassini;
+};
+
+__device__ __forceinline__ void lds_if(uint4& v, uint32_t addr, uint32_t take) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
+               : "r"(addr), "r"(take));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const FcParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_out,
+                                                                        const __grid_constant__ CUtensorMap tm_res) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms are 1024-byte aligned
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  uint8_t* slab_s = smem;                                  // 2 x kSlabBufBytes
+  uint8_t* b_s = slab_s + 2 * kSlabBufBytes;               // kFStages x kFBBytes
+  uint8_t* epi_s = b_s + kFStages * kFBBytes;              // kGatherWarps x 2 KB (32 pixels x 32 channels, 64-byte-swizzled)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_s + kGatherWarps * 2048);
+  uint64_t* full_bar = bars;                               // [kFStages] A slot written (16 warps) + weight slab landed (tx)
+  uint64_t* empty_bar = bars + kFStages;                   // [kFStages] the MMAs that read the slot have completed
+  uint64_t* sfull_bar = bars + 2 * kFStages;               // [2] slab landed (tx)
+  uint64_t* sempty_bar = bars + 2 * kFStages + 2;          // [2] slab consumed (16 warps)
+  uint64_t* tfull_bar = bars + 2 * kFStages + 4;           // [2] accumulator complete
+  uint64_t* tempty_bar = bars + 2 * kFStages + 6;          // [2] accumulator drained (16 warps)
+  uint64_t* res_bar = bars + 2 * kFStages + 8;             // [kGatherWarps] residual piece landed
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kFStages + 8 + kGatherWarps);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFStages; ++i) {
+      mbar_init(smem_u32(full_bar + i), kGatherWarps + 1);
+      mbar_init(smem_u32(empty_bar + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(sfull_bar + i), 1);
+      mbar_init(smem_u32(sempty_bar + i), kGatherWarps);
+      mbar_init(smem_u32(tfull_bar + i), 1);
+      mbar_init(smem_u32(tempty_bar + i), kGatherWarps);
+    }
+    for (int i = 0; i < kGatherWarps; ++i) mbar_init(smem_u32(res_bar + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kGatherWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const int HW = p.H * p.W;
+  const int nhalf = p.C / 64;
+  const int nst = 9 * nhalf;                     // stages per tile, HALF-major: all 9 taps of channels 0..63, then of 64..127
+  const int nfast = __ldg(p.hdr);
+  const int nitems = p.B * nfast;
+  const int4* info = reinterpret_cast<const int4*>(p.hdr + 4);
+  const int* flist = p.hdr + 4 + 4 * p.npos;
+  const int LEN = p.cassini ? p.H : p.W;
+
+  if (warp < kGatherWarps) {
+    // =================================================== gather producers (+ epilogue)
+    const int q = warp & 3, g = warp >> 2;       // TMEM lane quadrant; channel group: chunks 2g, 2g+1 of the stage's 8 (gather), output channels 32g.. (epilogue)
+    const int m = q * 32 + lane;                 // GEMM row = TMEM lane = pixel of the tile, short image axis fastest
+    const int mr = m >> p.tw_shift, mc = m & (p.tw - 1);
+    const int dW = p.cassini ? 1 : kSlabPitch, dH = p.cassini ? kSlabPitch : 1;  // slab pixel steps of the (row, col+1) and (row+1, col) corners
+    uint8_t* etile = epi_s + (size_t)warp * 2048;
+    const uint32_t slab_u32 = smem_u32(slab_s);
+    auto decode = [&](int item, int& b, int4& inf) {
+      b = item / nfast;
+      inf = __ldg(info + __ldg(flist + (item - b * nfast)));
+    };
+    auto epi_coords = [&](int b, const int4& inf, int& cx, int& cy) {
+      const int ty = inf.w >> 16, tx = inf.w & 0xffff;
+      cx = tx * p.tw, cy = b * p.H + ty * p.th + (32 >> p.tw_shift) * q;
+    };
+    // epilogue of one tile: TMEM lanes 32q.., accumulator columns 32g..32g+31 -> affine + residual + ReLU -> the warp's swizzled
+    // 2 KB tile -> TMA store.  Runs one stage into the NEXT tile's gather (double-buffered accumulator).
+    auto epilogue = [&](int item, uint32_t tn) {
+      int b;
+      int4 inf;
+      decode(item, b, inf);
+      const uint32_t buf = tn & 1;
+      mbar_wait(smem_u32(tfull_bar + buf), (tn >> 1) & 1);
+      tc_fence_after();
+      const int c0 = g * 32;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + buf * 128u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16), v);
+      if (p.has_res) mbar_wait(smem_u32(res_bar + warp), tn & 1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        uint8_t* ep = etile + lane * 64 + ((gg ^ ((lane >> 1) & 3)) << 4);
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[gg * 8 + e]);
+        if (p.scale) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + gg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + gg * 8) + 1);
+          y[0] *= s0.x, y[1] *= s0.y, y[2] *= s0.z, y[3] *= s0.w, y[4] *= s1.x, y[5] *= s1.y, y[6] *= s1.z, y[7] *= s1.w;
+        }
+        if (p.shift) {
+          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + gg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + gg * 8) + 1);
+          y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
+        }
+        if (p.has_res) {
+          const uint4 r = *reinterpret_cast<const uint4*>(ep);
+          const uint32_t r4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float r0, r1;
+            unpack2<FMT>(r4[e], r0, r1);
+            y[2 * e] += r0, y[2 * e + 1] += r1;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+        }
+        *reinterpret_cast<uint4*>(ep) = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        int cx, cy;
+        epi_coords(b, inf, cx, cy);
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_out), "r"(c0), "r"(cx), "r"(cy), "r"(smem_u32(etile))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
+    };
+
+    uint4 v1[2], v2[2], v3[2], v4[2];  // corner values (2 chunks each); loop carried: a skipped load leaves an older finite value, times weight 0
+#pragma unroll
+    for (int j = 0; j < 2; ++j) v1[j] = v2[j] = v3[j] = v4[j] = make_uint4(0, 0, 0, 0);
+    uint32_t stage = 0, tile_n = 0, slabn = 0;
+    int prev_item = -1;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tile_n) {
+      int b;
+      int4 inf;
+      decode(item, b, inf);
+      const int ty = inf.w >> 16, tx = inf.w & 0xffff, l0 = inf.x, s0 = inf.y;
+      const int pix = (ty * p.th + mr) * p.W + tx * p.tw + mc;  // this thread's pixel inside the image
+      int4 ent = __ldg(p.table + pix);                          // tap 0; later entries are prefetched one stage ahead
+      for (int hf = 0; hf < nhalf; ++hf, ++slabn) {
+        const uint32_t sb = slabn & 1;
+        const uint32_t slab = slab_u32 + sb * kSlabBufBytes;
+        mbar_wait(smem_u32(sfull_bar + sb), (slabn >> 1) & 1);
+        for (int k = 0; k < 9; ++k, ++stage) {
+          const int s = hf * 9 + k;
+          if (s == 1 && prev_item >= 0) epilogue(prev_item, tile_n - 1);
+          if (s == 4 && p.has_res && lane == 0) {
+            // this tile's residual piece -> the warp's epilogue tile (free once the previous tile's output store has read it)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            int cx, cy;
+            epi_coords(b, inf, cx, cy);
+            const uint32_t bar = smem_u32(res_bar + warp);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(etile)),
+                         "l"(&tm_res), "r"(g * 32), "r"(cx), "r"(cy), "r"(bar)
+                         : "memory");
+          }
+          // slab address of the top-left corner: line (long-axis coordinate - l0, modulo the axis: the grid wraps), then the short axis
+          const int hl = ent.w >> 16, wl = (int)(short)(ent.w & 0xffff);
+          int d = (p.cassini ? hl : wl) - l0;
+          d += d < 0 ? LEN : 0;
+          const int p1 = d * kSlabPitch + ((p.cassini ? wl : hl) - s0);
+          const uint32_t w12 = (uint32_t)ent.y, w34 = (uint32_t)ent.z;
+          const int kn = k == 8 ? 0 : k + 1;
+          if (s + 1 < nst) ent = __ldg(p.table + (size_t)kn * HW + pix);  // next stage's entry, in flight during the loads and the blend
+          {
+            const int pc[4] = {p1, p1 + dW, p1 + dH, p1 + dH + dW};
+            const uint32_t take[4] = {w12 & 0xffffu, w12 >> 16, w34 & 0xffffu, w34 >> 16};
+            uint4* vv[4] = {v1, v2, v3, v4};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // pixel pc[c] = 128 bytes; its 16-byte chunk cc sits at position cc ^ (pixel & 7) (TMA 128-byte swizzle); chunks 2g and
+              // 2g+1 are the two halves of one 32-byte pair
+              const uint32_t a = slab + (uint32_t)pc[c] * 128u + ((uint32_t)((2 * g) ^ (pc[c] & 7)) << 4);
+              lds_if(vv[c][0], a, take[c]);
+              lds_if(vv[c][1], a ^ 16u, take[c]);
+            }
+          }
+          const uint32_t slot = stage % kFStages, phase = (stage / kFStages) & 1;
+          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);  // the MMAs that read this A slot kFStages stages ago are complete
+          tc_fence_after();
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            o[4 * j + 0] = blend2<FMT>(w12, w34, v1[j].x, v2[j].x, v3[j].x, v4[j].x);
+            o[4 * j + 1] = blend2<FMT>(w12, w34, v1[j].y, v2[j].y, v3[j].y, v4[j].y);
+            o[4 * j + 2] = blend2<FMT>(w12, w34, v1[j].z, v2[j].z, v3[j].z, v4[j].z);
+            o[4 * j + 3] = blend2<FMT>(w12, w34, v1[j].w, v2[j].w, v3[j].w, v4[j].w);
+          }
+          // 16 channels of this pixel = 8 packed columns of TMEM lane m, A-operand slot `slot`
+          tmem_st8(tmem_base + kTmemAcc + slot * 32u + (uint32_t)(g * 8) + ((uint32_t)(q * 32) << 16), o);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(sempty_bar + sb));  // every load of this slab has been consumed by a blend
+      }
+      prev_item = item;
+    }
+    if (prev_item >= 0) epilogue(prev_item, tile_n - 1);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (warp == kGatherWarps + 1) {
+    // =================================================== weight loader: one 16 KB bulk copy per stage, up to kFStages ahead
+    if (lane == 0) {
+      uint32_t stage = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        for (int s = 0; s < nst; ++s, ++stage) {
+          const int hf = s / 9, k = s - hf * 9;
+          const uint32_t slot = stage % kFStages, phase = (stage / kFStages) & 1;
+          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
+          const uint32_t bar = smem_u32(full_bar + slot);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kFBBytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(b_s + (size_t)slot * kFBBytes)),
+                       "l"(p.wpk + (size_t)(k * nhalf + hf) * (kFBBytes / 2)), "r"(kFBBytes), "r"(bar)
+                       : "memory");
+        }
+      }
+    }
+  } else if (warp == kGatherWarps + 2) {
+    // =================================================== slab loader: one TMA box per line of the long axis, one (tile, half) ahead
+    if (lane == 0) {
+      uint32_t slabn = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int b = item / nfast;
+        const int4 inf = __ldg(info + __ldg(flist + (item - b * nfast)));
+        const int l0 = inf.x, s0 = inf.y, L = inf.z;
+        for (int hf = 0; hf < nhalf; ++hf, ++slabn) {
+          const uint32_t sb = slabn & 1;
+          mbar_wait(smem_u32(sempty_bar + sb), ((slabn >> 1) & 1) ^ 1);
+          const uint32_t bar = smem_u32(sfull_bar + sb);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(L * kSlabLineBytes) : "memory");
+          const uint32_t dst0 = smem_u32(slab_s) + sb * kSlabBufBytes;
+          for (int l = 0; l < L; ++l) {
+            int line = l0 + l;
+            line -= line >= LEN ? LEN : 0;  // the sampling grid wraps around the long axis (sphere_conv.py:225)
+            const int cw = p.cassini ? s0 : line, chh = p.cassini ? line : s0;
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst0 + l * kSlabPitchBytes),
+                         "l"(&tm_x), "r"(hf * 64), "r"(cw), "r"(chh), "r"(b), "r"(bar)
+                         : "memory");
+          }
+        }
+      }
+    }
+  } else {
+    // =================================================== MMA issuer (warp-uniform control flow, one elected lane issues)
+    const uint32_t idesc = make_idesc(128, FMT);
+    const uint32_t b_hi = desc_hi(128);
+    uint32_t stage = 0, tile_n = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tile_n) {
+      const uint32_t buf = tile_n & 1;
+      mbar_wait(smem_u32(tempty_bar + buf), ((tile_n >> 1) & 1) ^ 1);  // epilogue of tile - 2 has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * 128u;
+      for (int s = 0; s < nst; ++s, ++stage) {
+        const uint32_t slot = stage % kFStages, phase = (stage / kFStages) & 1;
+        mbar_wait(smem_u32(full_bar + slot), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = tmem_base + kTmemAcc + slot * 32u;                                  // 64 channels = 32 packed columns
+          const uint32_t b0 = desc_lo(smem_u32(b_s + (size_t)slot * kFBBytes), 128u * 16u);     // [8 chunks][128 rows][16 B]
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tacc, a0 + ks * 8u, b0 + ((uint32_t)(ks * 2 * 128 * 16) >> 4), b_hi, idesc, (s | ks) ? 1u : 0u);
+          umma_commit(smem_u32(empty_bar + slot));
+          if (s == nst - 1) umma_commit(smem_u32(tfull_bar + buf));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 }  // namespace
@@ -480,14 +915,38 @@ extern "C" int mode_sphere_conv_pack_weights(const float* w, mode_h16* w_packed,
   return MODE_OK;
 }
 
-extern "C" size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw) { return (size_t)16 * Kh * Kw * H * W; }
+// tile geometry of the slab kernel for an H x W map: 16 x 8 tiles when the long (wrapping) axis is the rows (Cassini), 8 x 16 when
+// it is the columns (ERP); 0 tile positions when the map is not tileable
+static void slab_tiling(int H, int W, int& th, int& tw, int& npos) {
+  th = H >= W ? 16 : 8, tw = H >= W ? 8 : 16;
+  npos = (H % th == 0 && W % tw == 0) ? (H / th) * (W / tw) : 0;
+}
+
+extern "C" size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw) {
+  int th, tw, npos;
+  slab_tiling(H, W, th, tw, npos);
+  return (size_t)16 * Kh * Kw * H * W + 16 + (size_t)npos * (16 + 4 + 4);  // entries | header | tile info | fast list | rest list
+}
 
 extern "C" int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, int fmt, void* stream) {
   MODE_CHECK_ARG(pos && table && H > 0 && W > 0 && Kh > 0 && Kw > 0, "sphere_conv_build_table: bad arguments");
   MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "sphere_conv_build_table: fmt must be 0 (bf16) or 1 (fp16)");
+  MODE_CHECK_ARG(H < 32768 && W < 32768, "sphere_conv_build_table: map too large");
+  (void)fmt;  // the table no longer depends on the storage format (fp16 blend weights for both)
+  cudaStream_t s = (cudaStream_t)stream;
   const long long n = (long long)Kh * Kw * H * W;
-  sphere_table_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(pos, (int4*)table, H, W, Kh * Kw, fmt);
+  sphere_table_kernel<<<ceil_div(n, 256), 256, 0, s>>>(pos, (int4*)table, H, W, Kh * Kw);
   MODE_CHECK_LAUNCH("sphere_conv_build_table");
+  int th, tw, npos;
+  slab_tiling(H, W, th, tw, npos);
+  int* hdr = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(table) + (size_t)16 * n);
+  int4* info = reinterpret_cast<int4*>(hdr + 4);
+  if (npos > 0 && Kh == 3 && Kw == 3) {
+    sphere_tileinfo_kernel<<<npos, 128, 0, s>>>((const int4*)table, info, H, W, Kh * Kw, th, tw);
+    MODE_CHECK_LAUNCH("sphere_conv_build_table (tile classes)");
+  }
+  sphere_tilelist_kernel<<<1, 32, 0, s>>>(info, hdr, hdr + 4 + 4 * npos, hdr + 4 + 5 * npos, (Kh == 3 && Kw == 3) ? npos : 0, th, tw);
+  MODE_CHECK_LAUNCH("sphere_conv_build_table (tile lists)");
   return MODE_OK;
 }
 
@@ -498,12 +957,54 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
   MODE_CHECK_ARG(B > 0 && H > 0 && W > 0, "sphere_conv_tc: bad shape");
   MODE_CHECK_ARG(C > 0 && C % 64 == 0, "sphere_conv_tc: C (%d) must be a multiple of 64 (use the f32 kernel otherwise)", C);
   MODE_CHECK_ARG(Co >= 64 && Co <= 256 && Co % 64 == 0, "sphere_conv_tc: Co (%d) must be 64, 128, 192 or 256", Co);
+  cudaStream_t cs = (cudaStream_t)stream;
   ScParams p;
   p.x = x, p.table = (const int4*)table, p.wpk = w_packed, p.scale = scale, p.shift = shift, p.res = residual, p.out = out;
   p.B = B, p.C = C, p.H = H, p.W = W, p.Co = Co, p.relu = relu;
   p.npix = (long long)B * H * W;
+  p.plist = nullptr, p.pcount = nullptr;
   MODE_CHECK_ARG((p.npix + W + 1) * C < 2147483647LL, "sphere_conv_tc: activation tensor too large for 32-bit offsets");
-  if (W % 16 == 0 && H % 8 == 0) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  // ---- slab kernel for every tile whose neighbourhood fits shared memory (all but the polar tile columns on a 256 x 128 map)
+  int th, tw, npos;
+  slab_tiling(H, W, th, tw, npos);
+  const int* hdr = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(table) + (size_t)16 * 9 * H * W);
+  static const bool slab_disabled = [] {
+    const char* e = getenv("MODE_B200_SPHERE_SLAB");  // diagnostics / A-B timing: MODE_B200_SPHERE_SLAB=0 forces the direct-gather kernel
+    return e != nullptr && e[0] == '0';
+  }();
+  const bool slab_ok = !slab_disabled && npos > 0 && Co == 128 && (C == 64 || C == 128) && aligned && B < 65536;
+  CUtensorMap tm_out, tm_res, tm_x;
+  memset(&tm_out, 0, sizeof(tm_out));
+  memset(&tm_res, 0, sizeof(tm_res));
+  if (slab_ok) {
+    int rc = make_epi_tmap(&tm_out, out, fmt, Co, W, (long long)B * H, tw);
+    if (rc == MODE_OK && residual) rc = make_epi_tmap(&tm_res, residual, fmt, Co, W, (long long)B * H, tw);
+    if (rc == MODE_OK) rc = make_slab_tmap(&tm_x, x, fmt, B, C, H, W, th > tw);
+    if (rc != MODE_OK) return rc;
+    FcParams f;
+    f.table = (const int4*)table, f.hdr = hdr, f.wpk = w_packed, f.scale = scale, f.shift = shift;
+    f.has_res = residual != nullptr, f.relu = relu, f.B = B, f.C = C, f.H = H, f.W = W, f.npos = npos;
+    f.th = th, f.tw = tw, f.tw_shift = tw == 8 ? 3 : 4, f.cassini = th > tw;
+    const size_t fsmem = 1024 + 2 * (size_t)kSlabBufBytes + (size_t)kFStages * kFBBytes + kGatherWarps * 2048 + (2 * kFStages + 8 + kGatherWarps) * 8 + 16;
+    static thread_local size_t fattr_dev[kMaxDevices] = {};
+    size_t& fattr = fattr_dev[current_device()];
+    if (fsmem > fattr) {
+      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_slab_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), "sphere_conv_tc (slab)");
+      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_slab_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), "sphere_conv_tc (slab)");
+      fattr = fsmem;
+    }
+    const int fgrid = std::min(B * npos, kNumSMs);
+    if (fmt == kFmtBF16)
+      sphere_conv_slab_kernel<kFmtBF16><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+    else
+      sphere_conv_slab_kernel<kFmtFP16><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+    MODE_CHECK_LAUNCH("sphere_conv_tc (slab)");
+    // the remaining tile positions go through the direct-gather kernel below, in list mode, with the same tile geometry
+    p.tw = tw, p.th = th, p.tiles_x = W / tw, p.tiles_y = H / th;
+    p.ntiles = B * npos;  // upper bound; the kernel reads the real count from the table
+    p.plist = hdr + 4 + 5 * npos, p.pcount = hdr + 1;
+  } else if (W % 16 == 0 && H % 8 == 0) {
     p.tw = 16, p.th = 8, p.tiles_x = W / 16, p.tiles_y = H / 8;
     p.ntiles = B * p.tiles_x * p.tiles_y;
   } else {
@@ -511,7 +1012,8 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
     p.ntiles = (int)((p.npix + 127) / 128);
   }
   const size_t smem = (size_t)kStagesS * (kABytes + (size_t)Co * 128) + 1024 + kGatherWarps * 2048 + (2 * kStagesS + 4 + kGatherWarps) * 8 + 16;
-  static thread_local size_t attr = 0;
+  static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
   if (smem > attr) {
     // one CTA per SM: leave the rest of the 228 KB to L1 -- the 9 taps x 4 corners of a tile re-read the same ~45 KB
     // of input, which must stay L1 resident (with a maximal carve-out the kernel was L2-bandwidth bound: 3.6 GB/launch)
@@ -524,27 +1026,24 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
     }
     attr = smem;
   }
-  // epilogue tiles through TMA: (Co, W, B*H) view of the NHWC output / residual, box 32 ch x 16 x 2, 64-byte swizzle
-  CUtensorMap tm_out, tm_res;
-  memset(&tm_out, 0, sizeof(tm_out));
-  memset(&tm_res, 0, sizeof(tm_res));
-  p.epi_tma = (p.tw == 16 && (Co == 64 || Co == 128) && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0) ? 1 : 0;
-  if (p.epi_tma) {
-    int rc = make_epi_tmap(&tm_out, out, fmt, Co, W, (long long)B * H);
-    if (rc == MODE_OK && residual) rc = make_epi_tmap(&tm_res, residual, fmt, Co, W, (long long)B * H);
+  // epilogue tiles through TMA: (Co, W, B*H) view of the NHWC output / residual, box 32 ch x tw x 32/tw, 64-byte swizzle
+  p.epi_tma = (p.tw != 0 && (Co == 64 || Co == 128) && aligned) ? 1 : 0;
+  if (p.epi_tma && !slab_ok) {
+    int rc = make_epi_tmap(&tm_out, out, fmt, Co, W, (long long)B * H, p.tw);
+    if (rc == MODE_OK && residual) rc = make_epi_tmap(&tm_res, residual, fmt, Co, W, (long long)B * H, p.tw);
     if (rc != MODE_OK) return rc;
   }
   const int grid = std::min(p.ntiles, kNumSMs);
   if (C == 128) {
     if (fmt == kFmtBF16)
-      sphere_conv_tc_kernel<kFmtBF16, 128><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+      sphere_conv_tc_kernel<kFmtBF16, 128><<<grid, kThreadsS, smem, cs>>>(p, tm_out, tm_res);
     else
-      sphere_conv_tc_kernel<kFmtFP16, 128><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+      sphere_conv_tc_kernel<kFmtFP16, 128><<<grid, kThreadsS, smem, cs>>>(p, tm_out, tm_res);
   } else {
     if (fmt == kFmtBF16)
-      sphere_conv_tc_kernel<kFmtBF16, 0><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+      sphere_conv_tc_kernel<kFmtBF16, 0><<<grid, kThreadsS, smem, cs>>>(p, tm_out, tm_res);
     else
-      sphere_conv_tc_kernel<kFmtFP16, 0><<<grid, kThreadsS, smem, (cudaStream_t)stream>>>(p, tm_out, tm_res);
+      sphere_conv_tc_kernel<kFmtFP16, 0><<<grid, kThreadsS, smem, cs>>>(p, tm_out, tm_res);
   }
   MODE_CHECK_LAUNCH("sphere_conv_tc");
   return MODE_OK;

@@ -264,7 +264,8 @@ extern "C" int mode_stem_conv_tc(const float* x0, const float* x1, const float* 
   rows = std::max(p.G, (rows + p.G - 1) / p.G * p.G);
   p.rows_strip = rows;
   p.strips = (p.Ho + rows - 1) / rows;
-  static thread_local size_t attr = 0;
+  static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
+  size_t& attr = attr_dev[current_device()];
   if (smem > attr) {
     MODE_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_tc_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem_conv_tc");
     MODE_CHECK_CUDA(cudaFuncSetAttribute(stem_conv_tc_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stem_conv_tc");

@@ -57,7 +57,7 @@ class ModeDisparity(nn.Module):
     self.maxdisp = maxdisp
     self.out_conf = out_conf
     self.sphereType = sphereType
-    self.precision = precision or os.environ.get('MODE_B200_PRECISION', 'bf16')
+    self.precision = precision or os.environ.get('MODE_B200_PRECISION', 'fp16')
     if self.precision not in ('fp32', 'bf16', 'fp16'):
       raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
     if conv == 'Regular':
@@ -88,7 +88,7 @@ class ModeDisparity(nn.Module):
       elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
         m.weight.data.fill_(1)
         m.bias.data.zero_()
-    self._plan = None
+    self._plan, self._plan_key = None, None
     self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_plan())
 
   # -------------------------------------------------------------------------------------------
@@ -96,6 +96,15 @@ class ModeDisparity(nn.Module):
   # -------------------------------------------------------------------------------------------
   def invalidate_plan(self):
     self._plan = None
+
+  def _weights_key(self):
+    """Cheap fingerprint of the weights a plan was folded from: storage addresses + in-place version counters."""
+    k = 0
+    for t in self.parameters():
+      k = (k * 1000003 + t._version + t.data_ptr()) & 0xFFFFFFFFFFFF
+    for t in self.buffers():
+      k = (k * 1000003 + t._version + t.data_ptr()) & 0xFFFFFFFFFFFF
+    return k
 
   def train(self, mode: bool = True):
     self._plan = None
@@ -125,8 +134,11 @@ class ModeDisparity(nn.Module):
       raise ValueError('maxdisp must be a multiple of 16')
     if self.training:
       return self._forward_train(left, right)
-    if self._plan is None:
-      self._plan = self._build_plan()
+    if torch.is_grad_enabled() and (left.requires_grad or right.requires_grad):
+      raise RuntimeError('ModeDisparity.eval() runs a fused, non-differentiable inference plan; call .train() for a differentiable forward')
+    key = self._weights_key()
+    if self._plan is None or self._plan_key != key:  # in-place weight edits (optimizer.step(), p.data.copy_()) bump tensor versions
+      self._plan, self._plan_key = self._build_plan(), key
     with torch.no_grad():
       pred3, conf = self._plan.run(left, right)
     if self.out_conf:

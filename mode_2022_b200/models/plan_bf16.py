@@ -13,18 +13,19 @@ import torch.nn.functional as F
 
 from .. import ops
 from .plan import _PlanBase, _w
-from .submodule import bn_affine
+from .submodule import bn_affine, bn_affine_host
 
 
 class _FoldedConv2d:
   """Conv2d + eval-BN folded into (bf16 channels_last weight, bias); cuDNN-backed."""
 
   def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype):
-    scale, shift = bn_affine(bn)
-    w = conv.weight.detach().float() * scale.view(-1, 1, 1, 1)
-    self.w = w.to(dtype).contiguous(memory_format=torch.channels_last)
-    self.shift = shift.float()
-    self.b = shift.to(dtype)
+    scale, shift = bn_affine_host(bn)  # folded on the host: no elementwise launches while a plan is built
+    dev = conv.weight.device
+    w = conv.weight.detach().float().cpu() * scale.view(-1, 1, 1, 1)
+    self.w = w.to(dtype).contiguous(memory_format=torch.channels_last).to(dev)
+    self.shift = shift.to(dev)
+    self.b = shift.to(dtype).to(dev)
     self.stride, self.padding, self.dilation = conv.stride, conv.padding, conv.dilation
 
   def move_bias_into(self, other: '_FoldedConv2d'):

@@ -8,6 +8,7 @@ same functional entry point `sphere_conv(input, position, weight, bias, stride, 
 """
 from __future__ import annotations
 
+import collections
 import math
 from functools import lru_cache
 
@@ -61,15 +62,24 @@ def sphere_position_numpy(height: int, width: int, sphere_type: str, Kh: int = 3
   return np.ascontiguousarray(grid.reshape(1, two * kh * kw, H, W))
 
 
-_DEVICE_POS = {}
+_DEVICE_POS = collections.OrderedDict()  # LRU-bounded: one grid per (resolution, projection, kernel, device) in use
+_DEVICE_POS_MAX = 16
 
 
 def sphere_position(height, width, sphere_type, Kh, Kw, device) -> torch.Tensor:
-  """Device-resident, shared copy of the grid (the reference keeps one copy per layer: 16 x 2.4 MB)."""
+  """Device-resident, shared copy of the grid (the reference keeps one copy per layer: 16 x 2.4 MB).  The upload is a
+  synchronous host-to-device copy of pageable memory, so the tensor is complete for every stream when this returns."""
   key = (height, width, sphere_type, Kh, Kw, str(device))
-  if key not in _DEVICE_POS:
-    _DEVICE_POS[key] = torch.from_numpy(sphere_position_numpy(height, width, sphere_type, Kh, Kw)).to(device)
-  return _DEVICE_POS[key]
+  pos = _DEVICE_POS.get(key)
+  if pos is None:
+    pos = _DEVICE_POS[key] = torch.from_numpy(sphere_position_numpy(height, width, sphere_type, Kh, Kw)).to(device)
+    if torch.device(device).type == 'cuda' and not torch.cuda.is_current_stream_capturing():
+      torch.cuda.current_stream(device).synchronize()
+    while len(_DEVICE_POS) > _DEVICE_POS_MAX:
+      _DEVICE_POS.popitem(last=False)
+  else:
+    _DEVICE_POS.move_to_end(key)
+  return pos
 
 
 def sphere_conv(input, position, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):

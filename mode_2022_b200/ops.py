@@ -10,7 +10,9 @@ There is no CPU implementation: calling an op on CPU tensors raises NotImplement
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import functools
 from typing import Optional
 
 import torch
@@ -25,7 +27,30 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def _stream():
+  """Current stream of the current device; every op runs under `_device_guard`, which makes the tensors' device current."""
   return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device_guard(fn):
+  """All CUDA tensor arguments must live on ONE device; that device is made current for the duration of the op, so the stream
+  handed to the C ABI, the output allocations and the library's per-device kernel attributes all belong to it (a model on
+  cuda:1 called while cuda:0 is current would otherwise launch on the wrong device)."""
+
+  @functools.wraps(fn)
+  def wrapper(*args, **kwargs):
+    dev = None
+    for a in list(args) + list(kwargs.values()):
+      if isinstance(a, torch.Tensor) and a.is_cuda:
+        if dev is None:
+          dev = a.device
+        elif a.device != dev:
+          raise RuntimeError(f'{fn.__name__}: tensor arguments live on different devices ({dev} and {a.device})')
+    if dev is None or dev.index == torch.cuda.current_device():
+      return fn(*args, **kwargs)
+    with torch.cuda.device(dev):
+      return fn(*args, **kwargs)
+
+  return wrapper
 
 
 def _chk(t: torch.Tensor, dtype, name: str):
@@ -58,6 +83,7 @@ def _fmt(dtype) -> int:
 
 
 @torch.library.custom_op('mode_b200::cost_volume', mutates_args=())
+@_device_guard
 def cost_volume(ref: torch.Tensor, tgt: torch.Tensor, d4: int) -> torch.Tensor:
   """fp32: (B,C,H,W) x2 -> (B,2C,D4,H,W)   [reference layout, models/mode_disparity.py:104-113]
   bf16/fp16: (B,H,W,C) x2 -> (B,D4,H,W,2C)   [NDHWC, consumed by the tensor-core conv3d]"""
@@ -86,6 +112,7 @@ def _(ref, tgt, d4):
   return ref.new_empty((B, d4, H, W, 2 * Cc))
 
 
+@_device_guard
 def costvol_conv_weights(weight: torch.Tensor, dtype=torch.bfloat16):
   """dres0[0] weight (32, 64, 3, 3, 3) fp32 -> the two (96, 288) GEMM operands of costvol_conv: row kh*32 + c, column
   (kd*3 + kw)*32 + o, rounded to the 16-bit storage format exactly like the implicit-GEMM weights."""
@@ -99,6 +126,7 @@ def costvol_conv_weights(weight: torch.Tensor, dtype=torch.bfloat16):
 
 
 @torch.library.custom_op('mode_b200::costvol_conv', mutates_args=())
+@_device_guard
 def costvol_conv(ref: torch.Tensor, tgt: torch.Tensor, wr: torch.Tensor, wt: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], d4: int,
                  relu: bool) -> torch.Tensor:
   """Cost volume + first 3-D conv (64 -> 32) + affine + ReLU without materialising the volume (costvol_conv.cu).
@@ -134,6 +162,7 @@ def _(ref, tgt, wr, wt, scale, shift, d4, relu):
 
 
 @torch.library.custom_op('mode_b200::disp_regress', mutates_args=())
+@_device_guard
 def disp_regress(cost: torch.Tensor, maxdisp: int, height: int, width: int) -> tuple[torch.Tensor, torch.Tensor]:
   """cost (B,1,D4,H4,W4) or (B,D4,H4,W4) fp32 -> (pred, conf), both (B,1,H,W) fp32
   (models/mode_disparity.py:143-183)."""
@@ -163,6 +192,7 @@ def _(cost, maxdisp, height, width):
 
 
 @torch.library.custom_op('mode_b200::sphere_conv_f32', mutates_args=())
+@_device_guard
 def sphere_conv_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                     residual: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
   """fp32 NCHW spherical conv with fused per-channel affine (+residual)(+ReLU).
@@ -191,6 +221,7 @@ def _(x, pos, weight, scale, shift, residual, relu):
   return x.new_empty((x.shape[0], weight.shape[0], x.shape[2], x.shape[3]))
 
 
+@_device_guard
 def sphere_conv_backward_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor, need_input: bool, need_weight: bool,
                              need_bias: bool):
   """Gradients of sphere_conv_f32 (plain semantics: scale=None, shift=bias): (grad_input, grad_weight, grad_bias), None where
@@ -209,6 +240,7 @@ def sphere_conv_backward_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.T
   return gi, gw, gb
 
 
+@_device_guard
 def sphere_conv_pack_weights(weight: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
   """(Co,C,3,3) fp32 -> 16-bit weight slabs [tap][C/64][8][Co][8] streamed by the tensor-core kernel."""
   weight = _chk(weight, torch.float32, 'sphere_conv_pack_weights')
@@ -220,25 +252,42 @@ def sphere_conv_pack_weights(weight: torch.Tensor, dtype=torch.bfloat16) -> torc
   return out
 
 
-_TABLES = {}
+_TABLES = collections.OrderedDict()  # (grid storage, shape, version, 16-bit format) -> (table, grid); LRU-bounded
+_TABLES_MAX = 16
 
 
+def _publish(stream_sync: bool = True):
+  """A cached constant built on the current stream may be consumed from any other stream later (HostPipeline's compute
+  stream, per-GPU threads): make it visible to all of them once, at creation (skipped inside a CUDA-graph capture, where
+  the warm-up pass has already built every entry)."""
+  if stream_sync and not torch.cuda.is_current_stream_capturing():
+    torch.cuda.current_stream().synchronize()
+
+
+@_device_guard
 def sphere_gather_table(pos: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
   """Pre-digested sampling grid for the tensor-core kernel (cached per grid tensor and 16-bit format): see
   mode_sphere_conv_build_table."""
   pos = _chk(pos, torch.float32, 'sphere_gather_table')
-  key = (pos.data_ptr(), tuple(pos.shape), pos._version, dtype)
-  if key not in _TABLES:
+  key = (pos.data_ptr(), tuple(pos.shape), pos._version, pos.device.index)  # the table does not depend on the 16-bit format
+  hit = _TABLES.get(key)
+  if hit is None:
     H, W = pos.shape[-2:]
     if pos.numel() != 18 * H * W:
       raise RuntimeError(f'invalid spatial size of position, expected 18x{H}x{W}, got {tuple(pos.shape)}')
     table = torch.empty(_lib.load().mode_sphere_conv_table_bytes(H, W, 3, 3), dtype=torch.uint8, device=pos.device)
     _lib.call('mode_sphere_conv_build_table', _p(pos), _p(table), H, W, 3, 3, _fmt(dtype), _stream())
-    _TABLES[key] = (table, pos)  # keep `pos` alive so the data_ptr key stays unique
-  return _TABLES[key][0]
+    _publish()
+    hit = _TABLES[key] = (table, pos)  # keeps `pos` alive while the entry lives, so the data_ptr key stays unique
+    while len(_TABLES) > _TABLES_MAX:
+      _TABLES.popitem(last=False)
+  else:
+    _TABLES.move_to_end(key)
+  return hit[0]
 
 
 @torch.library.custom_op('mode_b200::sphere_conv_bf16', mutates_args=())
+@_device_guard
 def sphere_conv_bf16(x: torch.Tensor, pos: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                      residual: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
   """NHWC bf16/fp16 spherical conv on tcgen05 tensor cores (gather fused into operand staging) + affine + residual
@@ -268,6 +317,7 @@ def _(x, pos, w_packed, cout, scale, shift, residual, relu):
 
 
 @torch.library.custom_op('mode_b200::stem_conv', mutates_args=())
+@_device_guard
 def stem_conv(x0: torch.Tensor, x1: Optional[torch.Tensor], weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], relu: bool,
               fp16: bool) -> torch.Tensor:
   """firstconv[0] of the MODE feature extractor (3 -> 32, 7x7, stride 2, pad 3) + affine + ReLU on tcgen05 tensor cores.
@@ -314,6 +364,7 @@ def conv3d_out_dims(d, h, w, mode):
 
 
 @torch.library.custom_op('mode_b200::conv3d_f32', mutates_args=())
+@_device_guard
 def conv3d_f32(x: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                residual: Optional[torch.Tensor], mode: int, relu: bool) -> torch.Tensor:
   """fp32 NCDHW 3x3x3 conv (mode 0/1) or transposed conv (mode 2) + affine + residual + ReLU
@@ -342,6 +393,7 @@ def _(x, weight, scale, shift, residual, mode, relu):
   return x.new_empty((B, Co, *conv3d_out_dims(D, H, W, mode)))
 
 
+@_device_guard
 def conv3d_pack_weights(weight: torch.Tensor, mode: int, dtype=torch.bfloat16) -> torch.Tensor:
   """fp32 PyTorch-layout 3x3x3 weights -> per-tap 16-bit tiles resident in shared memory."""
   weight = _chk(weight, torch.float32, 'conv3d_pack_weights')
@@ -353,6 +405,7 @@ def conv3d_pack_weights(weight: torch.Tensor, mode: int, dtype=torch.bfloat16) -
 
 
 @torch.library.custom_op('mode_b200::conv3d_bf16', mutates_args=())
+@_device_guard
 def conv3d_bf16(x: torch.Tensor, w_packed: torch.Tensor, cout: int, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
                 residual: Optional[torch.Tensor], mode: int, relu: bool, out_f32: bool) -> torch.Tensor:
   """NDHWC bf16/fp16 3x3x3 conv / strided conv / transposed conv on tcgen05 tensor cores with fused affine +
@@ -382,6 +435,7 @@ def _(x, w_packed, cout, scale, shift, residual, mode, relu, out_f32):
 
 
 @torch.library.custom_op('mode_b200::conv3d_classifier', mutates_args=())
+@_device_guard
 def conv3d_classifier(x: torch.Tensor, weight: torch.Tensor, residual: Optional[torch.Tensor]) -> torch.Tensor:
   """The 32 -> 1 classifier conv (3x3x3, pad 1, no bias) + fp32 residual as a pointwise tensor-core GEMM + shifted sum.
   x (B,D,H,W,32) bf16/fp16, weight (1,32,3,3,3) fp32, residual (B,D,H,W) fp32 or None -> (B,D,H,W) fp32."""
@@ -408,6 +462,7 @@ def _(x, weight, residual):
 # ------------------------------------------------------------------------------------------------
 
 
+@_device_guard
 def nchw_f32_to_nhwc_bf16(x: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
   """(B,C,*spatial) fp32 -> (B,*spatial,C) bf16 (or fp16 with dtype=torch.float16)."""
   x = _chk(x, torch.float32, 'nchw_f32_to_nhwc_bf16')
@@ -421,6 +476,7 @@ def nchw_f32_to_nhwc_bf16(x: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor
   return y
 
 
+@_device_guard
 def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
   """(B,*spatial,C) bf16/fp16 -> (B,C,*spatial) fp32."""
   x = _chk(x, x.dtype, 'nhwc_bf16_to_nchw_f32')
@@ -434,6 +490,7 @@ def nhwc_bf16_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
   return y
 
 
+@_device_guard
 def concat3_nhwc(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
   """Channel concatenation of three NHWC 16-bit maps (B,H,W,Ca|Cb|Cc) -> (B,H,W,Ca+Cb+Cc): a streaming copy kernel."""
   a = _chk(a, a.dtype, 'concat3_nhwc')
@@ -453,6 +510,7 @@ def concat3_nhwc(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Ten
 # ------------------------------------------------------------------------------------------------
 
 
+@_device_guard
 def disp_to_depth(disp: torch.Tensor, phi_l: torch.Tensor, baseline: float, want_f64: bool = False):
   """disp (...,H,W) fp32 -> depth fp32 [, depth fp64 (un-rounded, for the forward warp)]."""
   disp = _chk(disp, torch.float32, 'disp_to_depth')
@@ -466,6 +524,7 @@ def disp_to_depth(disp: torch.Tensor, phi_l: torch.Tensor, baseline: float, want
   return (out, out64) if want_f64 else out
 
 
+@_device_guard
 def grid_sample_border(src: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
   """src (N,C,Hs,Ws) fp32, grid (Ho,Wo,2) fp32 shared by the batch -> (N,C,Ho,Wo)."""
   src = _chk(src, torch.float32, 'grid_sample_border')
@@ -479,6 +538,7 @@ def grid_sample_border(src: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
   return out
 
 
+@_device_guard
 def depth_view_trans(depth: torch.Tensor, conf: torch.Tensor, sin_phi, cos_phi, sin_theta, cos_theta, Rt) -> tuple[torch.Tensor, torch.Tensor]:
   """depth (B,H,W) fp32 or fp64, conf (B,H,W) fp32; tables fp32 on device; Rt: 12 python floats (R row-major, then t)."""
   if depth.dtype not in (torch.float32, torch.float64):

@@ -57,13 +57,16 @@ class HostPipeline:
         with torch.cuda.graph(self.graph):
           self._g_out = model(self._g_left, self._g_right)
       torch.cuda.synchronize(self.dev)
+    self._plan, self._plan_key = model._plan, model._plan_key  # the captured graph holds THESE folded weights
 
   def submit(self, left_host: torch.Tensor, right_host: torch.Tensor) -> int:
     """Queue one frame (asynchronous); host tensors must stay untouched until the ticket is collected."""
+    if self.graph is not None and (self.model._plan is not self._plan or self.model._weights_key() != self._plan_key):
+      raise RuntimeError('HostPipeline: the model weights changed after the CUDA graph was captured; build a new HostPipeline')
     t, k = self.n, self.n % self.depth
     self.n += 1
-    cur = torch.cuda.current_stream(self.dev)
-    with torch.no_grad():
+    with torch.no_grad(), torch.cuda.device(self.dev):
+      cur = torch.cuda.current_stream(self.dev)
       self.s_in.wait_event(self.ev_cmp[k])  # the frame that used this slot `depth` submits ago has consumed its inputs
       with torch.cuda.stream(self.s_in):
         self.d_left[k].copy_(left_host, non_blocking=True)

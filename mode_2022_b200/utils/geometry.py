@@ -11,6 +11,7 @@ generated once on the host in numpy (fp64 -> fp32 exactly as the reference does)
 """
 from __future__ import annotations
 
+import collections
 import math
 from functools import lru_cache
 
@@ -78,14 +79,22 @@ def _c2e_grid_host(ca_h, ca_w):
   return np.ascontiguousarray(np.stack([gx, gy], axis=-1))
 
 
-_DEV = {}
+_DEV = collections.OrderedDict()  # constant grids / trig tables on the device, LRU-bounded
+_DEV_MAX = 64
 
 
 def _dev(key, make, device):
   k = (key, str(device))
-  if k not in _DEV:
-    _DEV[k] = torch.from_numpy(np.ascontiguousarray(make())).to(device)
-  return _DEV[k]
+  t = _DEV.get(k)
+  if t is None:
+    t = _DEV[k] = torch.from_numpy(np.ascontiguousarray(make())).to(device)
+    if not torch.cuda.is_current_stream_capturing():
+      torch.cuda.current_stream(device).synchronize()  # built once; complete for every stream that uses it later
+    while len(_DEV) > _DEV_MAX:
+      _DEV.popitem(last=False)
+  else:
+    _DEV.move_to_end(k)
+  return t
 
 
 def _as_device(x):

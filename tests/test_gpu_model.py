@@ -69,12 +69,13 @@ def _epe(a, b):
 
 
 # Measured precision budget (random-init network with calibrated BN = flat posteriors, the worst case for soft-argmin):
-#   3-D stack only, bf16 storage: 0.027-0.029 px EPE     3-D stack only, fp16 storage: 0.003-0.004 px EPE
-#   whole stage,    bf16 storage: 0.5-0.8 px  EPE         whole stage,    fp16 storage: 0.09-0.13  px EPE
-# (an fp32 CPU emulation that only rounds the stored activations reproduces these numbers: oracle experiment in DESIGN.md,
-#  i.e. the error is the storage format, not the kernels; the 2-D feature extractor dominates it).
-STACK_EPE = {'bf16': 0.05, 'fp16': 0.01}
-E2E_EPE = {'bf16': 1.5, 'fp16': 0.3}
+#   3-D stack only, fp16 storage: 0.003-0.005 px EPE     3-D stack only, bf16 storage: 0.027-0.029 px EPE
+#   whole stage,    fp16 storage: 0.09-0.17  px EPE      whole stage,    bf16 storage: 0.5-0.8 px  EPE
+# fp16 is the benchmarked 16-bit format (bench.py `dtype`): it meets north_star's 0.01 px conv3d budget.  bf16 (opt-in) cannot:
+# tools/precision_study.py shows the error is spread over every stored tensor (bf16 cost volume + dres0/1 alone: 0.015 px; keeping
+# the whole residual trunk in fp32: still 0.016 px) -- it is the 8-bit mantissa, not a kernel.  Bounds = ~2x the measured values.
+STACK_EPE = {'fp16': 0.01, 'bf16': 0.05}
+E2E_EPE = {'fp16': 0.3, 'bf16': 1.5}
 
 
 @pytest.mark.parametrize('precision', ['fp16', 'bf16'])
@@ -147,7 +148,11 @@ def test_two_stage_pipeline_in_memory():
   assert out.shape == (1, 1, H, W) and torch.isfinite(out).all() and out.min() >= 0 and out.max() <= 20.0
   # the uint8 confidence quantisation of the file pipeline (save_output_disparity_stage.py:199) can be emulated
   dq, cq = StageBoundary(quantise_conf=True)(disp, conf)
-  assert all(torch.equal(torch.round(c * 255), c * 255) or (torch.round(c * 255) - c * 255).abs().max() < 1e-3 for c in cq)
+  for c_q, c_raw, d_q, d_raw in zip(cq, confs, dq, depths):
+    lv = c_q * 255
+    assert (lv - torch.round(lv)).abs().max().item() < 1e-4 and lv.min().item() >= 0 and lv.max().item() <= 255  # exactly the 256 PNG levels
+    assert (c_q - c_raw.clamp(0, 1)).abs().max().item() <= 0.5 / 255 + 1e-6  # nearest level of the (saturated) confidence
+    assert torch.equal(d_q, d_raw)  # the depth maps travel as float32 npz in the reference: untouched
 
 
 def test_training_step_matches_reference_golden():
@@ -230,7 +235,7 @@ def test_fusion_matches_reference_golden(name):
   shapes = json.load(open(os.path.join(Hh.GOLD, 'mode_fusion_keys.json' if name == 'fusion' else 'baseline_keys.json')))
   depthes, confs, rgbs = Hh.fusion_inputs(64, 32, 4)
   cu = lambda ts: [t.cuda() for t in ts]
-  for precision, tol in (('fp32', 2e-4), ('bf16', 0.25)):
+  for precision, tol in (('fp32', 2e-4), ('bf16', 0.15)):
     m = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}, precision=precision) if name == 'fusion' else Baseline(20.0, precision=precision)
     assert {k: list(v.shape) for k, v in m.state_dict().items()} == shapes
     m.load_state_dict(O.synthetic_state_dict(shapes, seed=4))
@@ -239,4 +244,60 @@ def test_fusion_matches_reference_golden(name):
       y = m(cu(depthes), cu(confs), cu(rgbs)) if name == 'fusion' else m(cu(depthes))
     assert y.dtype == torch.float32 and y.shape == (1, 1, 64, 32)
     err = np.abs(y.cpu().numpy() - z[name]).max()
+    print(f'{name} {precision}: max abs err vs reference golden {err:.4f} (depth units, range [0, 20])')
     assert err <= tol, (precision, err)  # depth units on a [0, 20] range
+
+
+@pytest.mark.parametrize('precision,rel', [('fp16', 2e-2), ('bf16', 1.5e-1)])
+@pytest.mark.parametrize('name', ['tiny_cassini', 'tiny_erp', 'small_cassini'])
+def test_h16_feature_stage_vs_fp32_plan(name, precision, rel):
+  """The 16-bit feature extractor as a stage (stem kernel, BN/downsample-shift folding into cuDNN convs, tensor-core sphere conv,
+  concat3 kernel, lastconv) against the fp32 plan's features: a mis-wired layer or a wrong fold is O(1) away, rounding noise through
+  ~45 layers stays within a few 16-bit ulps of the feature range."""
+  from mode_2022_b200.models.plan import Fp32Plan
+  from mode_2022_b200.models.plan_bf16 import Bf16Plan
+  dtype = torch.float16 if precision == 'fp16' else torch.bfloat16
+  sd, (H, W, D, st, seed), z = Hh.golden_state_dict(name)
+  left, right = Hh.synth_inputs(H, W, seed)
+  p32, p16 = Fp32Plan(_model(name, 'fp32', sd, H, W, D, st)), Bf16Plan(_model(name, precision, sd, H, W, D, st), dtype)
+  with torch.no_grad():
+    f32 = p32.features(torch.cat([left, right]).cuda())
+    f16 = p16.features(left.cuda(), right.cuda()).float()
+  assert f16.shape == f32.shape == (2, 32, H // 4, W // 4)
+  scale = f32.abs().max().item()
+  err = (f16 - f32).abs()
+  print(f'{name} {precision}: feature stage max err {err.max().item() / scale:.2e} / mean {err.mean().item() / scale:.2e} of the feature range ({scale:.2f}); '
+        f'vs reference golden {np.abs(f32[:1].cpu().numpy() - z["feat_l"]).max():.1e}')
+  assert err.max().item() <= rel * scale and err.mean().item() <= rel * scale / 8
+
+
+def test_concat3_nhwc_bit_exact():
+  from mode_2022_b200 import ops
+  g = torch.Generator().manual_seed(3)
+  for dtype in (torch.float16, torch.bfloat16):
+    for (n, ca, cb, cc) in [((2, 16, 8), 64, 64, 128), ((1, 5, 7), 8, 16, 24), ((3, 1, 1), 128, 8, 64)]:
+      a, b, c = (torch.randn(*n, ch, generator=g).to(dtype).cuda() for ch in (ca, cb, cc))
+      out = ops.concat3_nhwc(a, b, c)
+      assert out.shape == (*n, ca + cb + cc) and torch.equal(out, torch.cat([a, b, c], -1))
+
+
+def test_ops_follow_the_tensors_device_not_the_current_one():
+  """A model on cuda:1 called while cuda:0 is current must launch on cuda:1: every op enters its tensors' device."""
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  from mode_2022_b200 import ops
+  sd, (H, W, D, st, seed), z = Hh.golden_state_dict('tiny_cassini')
+  left, right = Hh.synth_inputs(H, W, seed)
+  from mode_2022_b200.models import ModeDisparity
+  outs = []
+  for dev in ('cuda:0', 'cuda:1'):
+    m = ModeDisparity(D, in_height=H, in_width=W, sphereType=st, out_conf=True, precision='fp16')
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    with torch.cuda.device(0):
+      pred, conf = m(left.to(dev), right.to(dev))
+    assert pred.device == torch.device(dev)
+    outs.append(pred.cpu())
+  assert torch.equal(outs[0], outs[1])
+  with pytest.raises(RuntimeError):
+    ops.cost_volume(torch.zeros(1, 8, 4, 4, device='cuda:0'), torch.zeros(1, 8, 4, 4, device='cuda:1'), 1)

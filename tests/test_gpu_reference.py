@@ -1,0 +1,125 @@
+"""GPU parity against the PRIMARY oracle of SURVEY.md section 8c: the UNMODIFIED reference (its Python + its own compiled CUDA
+extension, staged under baseline/_ref/ref by oracle/stage_reference.py) executed on the same B200, TF32 off.
+
+  * whole-model fp32 parity at BASELINE config[0] (512x256 Cassini / 256x512 ERP, D=64) and config[1]'s shape (1024x512, D=192);
+  * the 16-bit plan against the same reference output (EPE);
+  * operator-level drop-in proof: the reference's own SphereConvFunction / ModeDisparity Python running
+    on mode_2022_b200/integration/sphere_conv_cuda.py (ctypes over libmode_b200.so) instead of its pybind module.
+
+The weights are the key-addressed synthetic state dict, BN statistics calibrated BY THE REFERENCE ITSELF (one train-mode pass
+with momentum=None), so that the un-trained network is not saturated.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mode_oracle as O
+from oracle import stage_reference as SR
+from tests import helpers as Hh
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not SR.available(), reason='baseline/_ref/ref not staged (python oracle/stage_reference.py)')]
+
+
+@pytest.fixture(scope='module')
+def ref_pkg():
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  return SR.reference_package()
+
+
+def _calibrated_reference(pkg, H, W, D, st, seed, out_conf=True):
+  """Reference ModeDisparity on the GPU with synthetic weights and reference-calibrated BN; returns (model, left, right)."""
+  m = pkg.ModeDisparity(D, conv='Sphere', in_height=H, in_width=W, sphereType=st, out_conf=out_conf)
+  m.load_state_dict(O.synthetic_state_dict(Hh.KEY_SHAPES, seed=seed))
+  m = m.cuda()
+  left, right = (t.cuda() for t in Hh.synth_inputs(H, W, seed))
+  for mod in m.modules():
+    if isinstance(mod, (torch.nn.BatchNorm2d, torch.nn.BatchNorm3d)):
+      mod.momentum = None
+      mod.reset_running_stats()
+  m.train()
+  with torch.no_grad():
+    m(left, right)
+  return m.eval(), left, right
+
+
+def _ours(m_ref, H, W, D, st, precision):
+  from mode_2022_b200.models import ModeDisparity
+  m = ModeDisparity(D, conv='Sphere', in_height=H, in_width=W, sphereType=st, out_conf=True, precision=precision)
+  m.load_state_dict(m_ref.state_dict())
+  return m.cuda().eval()
+
+
+CONFIGS = [(512, 256, 64, 'Cassini', 31), (256, 512, 64, 'ERP', 32), (1024, 512, 192, 'Cassini', 33)]
+
+
+@pytest.mark.parametrize('H,W,D,st,seed', CONFIGS)
+def test_fp32_plan_matches_unmodified_reference_on_gpu(ref_pkg, H, W, D, st, seed):
+  """north_star: fp32 disparity within 1e-4 relative of the reference PyTorch path, on identical inputs and weights, same GPU."""
+  m_ref, left, right = _calibrated_reference(ref_pkg, H, W, D, st, seed)
+  with torch.no_grad():
+    pred_r, conf_r = m_ref(left, right)
+    pred, conf = _ours(m_ref, H, W, D, st, 'fp32')(left, right)
+  assert pred.shape == pred_r.shape == (1, 1, H, W) and conf.shape[-2:] == conf_r.shape[-2:]
+  rel = ((pred - pred_r).abs() / pred_r.abs().clamp_min(1.0)).max().item()
+  epe = (pred - pred_r).abs().mean().item()
+  same_r = torch.round(pred) == torch.round(pred_r)
+  e_conf = ((conf.reshape(-1) - conf_r.reshape(-1)).abs() * same_r.reshape(-1)).max().item()
+  spread = pred_r.std().item()
+  print(f'[ref-gpu] {H}x{W} D={D} {st}: fp32 plan vs unmodified reference: max rel {rel:.2e}, EPE {epe:.2e} px, conf {e_conf:.2e}, same-bin {same_r.float().mean().item():.5f}, '
+        f'reference disparity std {spread:.2f} px')
+  assert spread > 0.5, 'fixture is saturated'
+  assert rel <= 2e-4 and epe <= 2e-5, (rel, epe)
+  assert same_r.float().mean().item() > 0.999 and e_conf <= 2e-4
+
+
+@pytest.mark.parametrize('precision,bound', [('fp16', 0.3), ('bf16', 1.5)])
+def test_h16_plan_vs_unmodified_reference_full_size(ref_pkg, precision, bound):
+  """The benchmarked configuration (1024x512, D=192): 16-bit tensor-core plan against the reference's fp32 output."""
+  H, W, D, st, seed = CONFIGS[2]
+  m_ref, left, right = _calibrated_reference(ref_pkg, H, W, D, st, seed)
+  with torch.no_grad():
+    pred_r, _ = m_ref(left, right)
+    pred, conf = _ours(m_ref, H, W, D, st, precision)(left, right)
+  epe = (pred - pred_r).abs().mean().item()
+  print(f'[ref-gpu] {H}x{W} D={D}: {precision} plan vs unmodified reference EPE {epe:.4f} px (max {(pred - pred_r).abs().max().item():.3f})')
+  assert torch.isfinite(pred).all() and torch.isfinite(conf).all()
+  assert epe <= bound, epe
+
+
+def test_reference_python_runs_on_libmode_b200_shim(ref_pkg):
+  """INTEGRATION.md section 2, executed: the reference's own Python (SphereConv / SphereConvFunction, forward AND backward,
+  then the whole ModeDisparity) with its pybind module `sphere_conv_cuda` replaced by the ctypes binding of libmode_b200."""
+  from mode_2022_b200.integration import sphere_conv_cuda as shim
+  pkg_shim = SR.reference_package(native_op=shim)
+  assert pkg_shim is not ref_pkg
+  for (B, C, Co, h, w, st) in [(2, 64, 128, 64, 32, 'Cassini'), (1, 128, 128, 32, 64, 'ERP')]:
+    g = torch.Generator().manual_seed(C + h)
+    x = torch.randn(B, C, h, w, generator=g).cuda()
+    gout = torch.randn(B, Co, h, w, generator=g).cuda()
+    outs = []
+    for pkg in (ref_pkg, pkg_shim):
+      SphereConv = pkg.initModel.SphereConv
+      torch.manual_seed(5)
+      layer = SphereConv(h, w, st, C, Co, 3, stride=1, padding=1).cuda()
+      xi = x.clone().requires_grad_()
+      y = layer(xi)
+      y.backward(gout)
+      outs.append((y.detach(), xi.grad.detach(), layer.weight.grad.detach()))
+    for name, a, b, tol in zip(('output', 'grad_input', 'grad_weight'), outs[0], outs[1], (2e-5, 5e-5, 5e-5)):
+      err = (a - b).abs().max().item()
+      assert err <= tol * max(1.0, a.abs().max().item()), (name, err)
+  # whole reference model, eval: the shim-backed copy reproduces the compiled-extension copy
+  H, W, D, st, seed = 256, 128, 32, 'Cassini', 34
+  m_ref, left, right = _calibrated_reference(ref_pkg, H, W, D, st, seed)
+  m_shim = pkg_shim.ModeDisparity(D, conv='Sphere', in_height=H, in_width=W, sphereType=st, out_conf=True)
+  m_shim.load_state_dict(m_ref.state_dict())
+  m_shim = m_shim.cuda().eval()
+  with torch.no_grad():
+    (p0, c0), (p1, c1) = m_ref(left, right), m_shim(left, right)
+  rel = ((p0 - p1).abs() / p0.abs().clamp_min(1.0)).max().item()
+  print(f'[ref-gpu] reference Python over libmode_b200 shim vs over its own extension: max rel {rel:.2e}')
+  assert rel <= 1e-4, rel
+  # the shim reports errors the way the C ABI does (the reference op would TORCH_CHECK): stride 2 is not built
+  with pytest.raises(RuntimeError):
+    shim.sphere_conv_forward_cuda(x, torch.empty(8, 64, 3, 3).cuda(), x, x, x, x, x, 3, 3, 2, 2, 1, 1, 1, 1, 1, False)

@@ -79,3 +79,34 @@ def test_cpu_tensors_fail_loudly_in_both_modes():
     m.train(mode)
     with pytest.raises(NotImplementedError):
       m(torch.zeros(1, 3, 64, 32), torch.zeros(1, 3, 64, 32))
+
+
+def test_bench_roofline_report_classes():
+  """bench.py's per-kernel roofline bookkeeping (pure host logic): C-ABI argument lists -> algorithmic FLOPs / bytes -> binding bound."""
+  import ctypes as C
+  import bench
+
+  class Ev:
+    def __init__(self, t):
+      self.t = t
+
+    def elapsed_time(self, other):
+      return other.t - self.t
+
+  vp = lambda: C.c_void_p(1234)
+  prof = []
+  for _ in range(2):
+    prof.append(('mode_conv3d_tc', (vp(), vp(), vp(), vp(), None, None, vp(), None, 6, 32, 32, 48, 256, 128, 0, 1, 1, vp()), Ev(0.0), Ev(0.45)))
+    prof.append(('mode_conv3d_tc', (vp(), vp(), vp(), vp(), vp(), None, vp(), None, 6, 64, 32, 24, 128, 64, 2, 1, 1, vp()), Ev(0.0), Ev(0.27)))
+    prof.append(('mode_conv3d_classifier_tc', (vp(), vp(), None, vp(), 6, 48, 256, 128, 1, vp()), Ev(0.0), Ev(0.2)))
+    prof.append(('mode_sphere_conv_tc', (vp(), vp(), vp(), vp(), vp(), vp(), vp(), 12, 128, 256, 128, 128, 1, 1, vp()), Ev(0.0), Ev(0.2)))
+    prof.append(('mode_disp_regress', (vp(), vp(), vp(), 6, 48, 256, 128, 192, 1024, 512, vp()), Ev(0.0), Ev(0.39)))
+    prof.append(('mode_costvol_conv_fused', (vp(), vp(), vp(), vp(), vp(), 6, 48, 256, 128, 1, 1, vp()), Ev(0.0), Ev(0.36)))
+  r = bench.roofline_report(prof, 2)
+  assert r['bound'] == 'tensor' and r['launches_per_step'] == 3 and 0 < r['frac'] < 1.5
+  by = {k['kernel']: k for k in r['kernels']}
+  s1 = by['conv3d_tc 32->32 s1 @48x256x128']
+  assert s1['bound'] == 'tensor' and abs(s1['TFLOPs'] - 2 * 27 * 32 * 32 * 6 * 48 * 256 * 128 / 0.45e-3 / 1e12) < 1.0
+  assert by['conv3d_tc 64->32 deconv @24x128x64']['bound'] == 'hbm'           # 1.3 GB moved: HBM-bound, not tensor-bound
+  assert by['disp_regress (upsample + softmax + soft-argmin + confidence)']['bound'] == 'mufu_exp'
+  assert by['sphere_conv_tc 128->128 @256x128']['launches_per_step'] == 1
