@@ -220,7 +220,9 @@ def reference_gpu_block(dev):
       return {'unavailable': 'baseline/_ref/ref is not staged on this box (python oracle/stage_reference.py)'}
     tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False  # torch defaults = what a reference user gets
-    m = pkg.ModeDisparity(MAXDISP, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', out_conf=True)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the reference's constructors print(); stdout carries exactly one JSON line
+      m = pkg.ModeDisparity(MAXDISP, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', out_conf=True)
     m.load_state_dict(O.synthetic_state_dict(KEY_SHAPES, seed=0))
     m = m.to(dev).eval()
     g = torch.Generator().manual_seed(0)

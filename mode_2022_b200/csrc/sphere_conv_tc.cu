@@ -84,13 +84,19 @@ struct ScParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// arrive from lane 0 only, as a predicated instruction (an `if (lane == 0)` costs a divergence region per use)
+__device__ __forceinline__ void mbar_arrive_lane0(uint32_t bar, int lane) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(bar), "r"(lane) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+template <bool BACKOFF = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (BACKOFF) __nanosleep(64);  // producer threads far ahead of their consumer: do not steal issue slots from the gather warps
     if (it > (1u << 24)) {
       printf("sphere_conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
@@ -454,11 +460,17 @@ __global__ void sphere_table_kernel(const float* __restrict__ pos, int4* __restr
 // Tiles with L <= kSlabLines whose short extent fits go to the slab kernel ("fast"), the rest (the polar tile columns, where
 // one tap reaches half-way round the sphere) to the direct-gather kernel above.
 constexpr int kSlabShort = 12;                        // tile short side 8 + 2 + 2: taps reach [-2, +2] columns (rows for ERP)
-constexpr int kSlabLineBytes = kSlabShort * 128;      // one line of the slab: 12 pixels x 64 channels x 2 B
-constexpr int kSlabLines = 32;                        // 16 + 2 * 8: footprints up to +-7.5 lines
-constexpr int kSlabBytes = kSlabLines * kSlabLineBytes;  // 49152 per (tile, channel half), 1024-aligned
+constexpr int kSlabLineBytes = kSlabShort * 128;      // one LOADED line of the slab: 12 pixels x 64 channels x 2 B
+// Slab line pitch in pixels and line capacity, by orientation.  Gather lanes of a quarter-warp are 8 neighbouring pixels along the
+// SHORT axis for a Cassini map: a pitch that is a multiple of 8 pixels makes their eight 16-byte swizzle positions distinct even
+// when neighbouring columns sample different lines (the footprint grows towards the poles), i.e. conflict-free LDS.128.  For an
+// ERP map the lanes run along the long axis (one LINE per lane): an odd pitch walks the eight positions instead.
+__host__ __device__ constexpr int slab_pitch(bool cassini) { return cassini ? 16 : 13; }
+__host__ __device__ constexpr int slab_lines(bool cassini) { return cassini ? 28 : 32; }   // 16 + 2*6: footprints up to +-5.8 lines (7.5 for ERP)
+constexpr int kSlabBufBytes = 28 * 16 * 128;          // 57344 per (tile, channel half) >= 32 * 13 * 128, 1024-aligned
 
 __global__ void sphere_tileinfo_kernel(const int4* __restrict__ table, int4* __restrict__ info, int H, int W, int KK, int TH, int TW) {
+  const int kSlabLines = slab_lines(TH > TW);
   __shared__ int s_min_l, s_max_l, s_min_s, s_max_s, s_bad;
   const int tiles_x = W / TW;
   const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
@@ -491,7 +503,9 @@ __global__ void sphere_tileinfo_kernel(const int4* __restrict__ table, int4* __r
     int4 r = make_int4(0, 0, 0, (ty << 16) | tx);  // z = 0: not a slab tile
     if (s_max_l < s_min_l) {
       r.z = 1;  // no tap at all in this tile: one (unused) line
-    } else if (!s_bad && s_max_l - s_min_l + 1 <= kSlabLines && s_max_s - s_min_s + 1 <= kSlabShort) {
+    } else if (!s_bad && s_max_l - s_min_l + 1 <= kSlabLines && 2 * (s_max_l - s_min_l + 1) <= LEN && s_max_s - s_min_s + 1 <= kSlabShort) {
+      // (2L <= LEN: the lines of the slab are distinct and consecutive modulo the axis length, so the (line + 1) corner of a tap is
+      //  the NEXT slab line; a footprint that wraps more than half-way round a small map goes to the direct-gather kernel)
       int l0 = (tl0 + s_min_l) % LEN;
       if (l0 < 0) l0 += LEN;
       r.x = l0, r.y = s_min_s, r.z = s_max_l - s_min_l + 1;
@@ -595,10 +609,6 @@ int make_slab_tmap(CUtensorMap* tm, const void* ptr, int fmt, int B, int C, int 
 constexpr int kFStages = 5;                              // ring depth: A slots in TMEM (32 columns each) and weight slabs in smem
 constexpr int kFThreads = (kGatherWarps + 3) * 32;       // 16 gather/epilogue warps, MMA warp, weight loader, slab loader
 constexpr int kFBBytes = 128 * 64 * 2;                   // one weight slab: Co = 128 x 64 channels
-constexpr int kSlabPitch = 13;                           // pixels per slab line (12 loaded + 1 pad): odd, so that steps of one LINE also
-                                                         // walk all eight 16-byte positions of the 128-byte swizzle (ERP lanes)
-constexpr int kSlabPitchBytes = kSlabPitch * 128;
-constexpr int kSlabBufBytes = ((kSlabLines * kSlabPitchBytes) + 1023) & ~1023;  // 53248
 constexpr int kTmemAcc = 256;                            // two 128-column accumulators, then the A ring
 
 struct FcParams {
@@ -622,6 +632,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
                "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem descriptor]
 __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -630,48 +645,50 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_
       : "memory");
 }
 
-template <int FMT>
+template <int FMT, int CASSINI>
 __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const FcParams p, const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_out,
                                                                         const __grid_constant__ CUtensorMap tm_res) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // swizzle atoms are 1024-byte aligned
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  uint8_t* slab_s = smem;                                  // 2 x kSlabBufBytes
-  uint8_t* b_s = slab_s + 2 * kSlabBufBytes;               // kFStages x kFBBytes
-  uint8_t* epi_s = b_s + kFStages * kFBBytes;              // kGatherWarps x 2 KB (32 pixels x 32 channels, 64-byte-swizzled)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_s + kGatherWarps * 2048);
-  uint64_t* full_bar = bars;                               // [kFStages] A slot written (16 warps) + weight slab landed (tx)
-  uint64_t* empty_bar = bars + kFStages;                   // [kFStages] the MMAs that read the slot have completed
-  uint64_t* sfull_bar = bars + 2 * kFStages;               // [2] slab landed (tx)
-  uint64_t* sempty_bar = bars + 2 * kFStages + 2;          // [2] slab consumed (16 warps)
-  uint64_t* tfull_bar = bars + 2 * kFStages + 4;           // [2] accumulator complete
-  uint64_t* tempty_bar = bars + 2 * kFStages + 6;          // [2] accumulator drained (16 warps)
-  uint64_t* res_bar = bars + 2 * kFStages + 8;             // [kGatherWarps] residual piece landed
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 2 * kFStages + 8 + kGatherWarps);
+  // shared-memory map (byte offsets from a 1024-aligned base: TMA swizzle atoms are 1024-byte aligned); all addressing below is
+  // 32-bit shared-window arithmetic on `sm`
+  const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kOffB = 2 * kSlabBufBytes;                    // weight ring: kFStages x kFBBytes
+  constexpr uint32_t kOffEpi = kOffB + kFStages * kFBBytes;        // kGatherWarps x 2 KB epilogue tiles (32 pixels x 32 channels, 64-byte-swizzled)
+  constexpr uint32_t kOffBar = kOffEpi + kGatherWarps * 2048;
+  const uint32_t full_bar = sm + kOffBar;                          // [kFStages] A slot written (8 warps) + weight slab landed (tx)
+  const uint32_t empty_bar = full_bar + 8 * kFStages;              // [kFStages] the MMAs that read the slot have completed
+  const uint32_t sfull_bar = empty_bar + 8 * kFStages;             // [2] slab landed (tx)
+  const uint32_t sempty_bar = sfull_bar + 16;                      // [2] slab consumed (16 warps)
+  const uint32_t tfull_bar = sempty_bar + 16;                      // [2] accumulator complete
+  const uint32_t tempty_bar = tfull_bar + 16;                      // [2] accumulator drained (16 warps)
+  const uint32_t res_bar = tempty_bar + 16;                        // [kGatherWarps] residual piece landed
+  const uint32_t tmem_ptr_u32 = res_bar + 8 * kGatherWarps;
+  uint8_t* const sm_gen = smem_raw + (sm - smem_u32(smem_raw));    // generic pointer to the aligned base
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFStages; ++i) {
-      mbar_init(smem_u32(full_bar + i), kGatherWarps + 1);
-      mbar_init(smem_u32(empty_bar + i), 1);
+      mbar_init(full_bar + 8 * i, kGatherWarps / 2 + 1);
+      mbar_init(empty_bar + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(sfull_bar + i), 1);
-      mbar_init(smem_u32(sempty_bar + i), kGatherWarps);
-      mbar_init(smem_u32(tfull_bar + i), 1);
-      mbar_init(smem_u32(tempty_bar + i), kGatherWarps);
+      mbar_init(sfull_bar + 8 * i, 1);
+      mbar_init(sempty_bar + 8 * i, kGatherWarps);
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, kGatherWarps);
     }
-    for (int i = 0; i < kGatherWarps; ++i) mbar_init(smem_u32(res_bar + i), 1);
+    for (int i = 0; i < kGatherWarps; ++i) mbar_init(res_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kGatherWarps) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_u32), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t tmem_base = *reinterpret_cast<const uint32_t*>(sm_gen + (tmem_ptr_u32 - sm));
   const int HW = p.H * p.W;
   const int nhalf = p.C / 64;
   const int nst = 9 * nhalf;                     // stages per tile, HALF-major: all 9 taps of channels 0..63, then of 64..127
@@ -679,17 +696,26 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
   const int nitems = p.B * nfast;
   const int4* info = reinterpret_cast<const int4*>(p.hdr + 4);
   const int* flist = p.hdr + 4 + 4 * p.npos;
-  const int LEN = p.cassini ? p.H : p.W;
+  const int LEN = CASSINI ? p.H : p.W;
+  constexpr int kSlabPitch = slab_pitch(CASSINI != 0), kSlabPitchBytes = kSlabPitch * 128;
+  const int my_tiles = (int)blockIdx.x < nitems ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp < kGatherWarps) {
     // =================================================== gather producers (+ epilogue)
-    const int q = warp & 3, g = warp >> 2;       // TMEM lane quadrant; channel group: chunks 2g, 2g+1 of the stage's 8 (gather), output channels 32g.. (epilogue)
+    // Gather role: the 16 warps form two sets; set 0 produces the even stages of the CTA's stage sequence, set 1 the odd ones, so a
+    // stage is written by 8 warps = 4 TMEM lane quadrants (32 pixels each) x 2 channel groups (4 chunks = 32 channels = 16 packed
+    // TMEM columns each): per (pixel, tap) ONE table entry, ONE address computation and ONE tcgen05.st serve 32 channels.
+    // Epilogue role: all 16 warps, lane quadrant q x output-channel group eg (32 channels).
+    const int q = warp & 3, g = (warp >> 2) & 1, set = warp >> 3, eg = warp >> 2;
     const int m = q * 32 + lane;                 // GEMM row = TMEM lane = pixel of the tile, short image axis fastest
     const int mr = m >> p.tw_shift, mc = m & (p.tw - 1);
-    const int dW = p.cassini ? 1 : kSlabPitch, dH = p.cassini ? kSlabPitch : 1;  // slab pixel steps of the (row, col+1) and (row+1, col) corners
-    uint8_t* etile = epi_s + (size_t)warp * 2048;
-    const uint32_t slab_u32 = smem_u32(slab_s);
-    auto decode = [&](int item, int& b, int4& inf) {
+    constexpr int dW = CASSINI ? 1 : kSlabPitch, dH = CASSINI ? kSlabPitch : 1;  // slab pixel steps of the (row, col+1) and (row+1, col) corners
+    const uint32_t etile = sm + kOffEpi + (uint32_t)warp * 2048u;
+    uint8_t* const etile_gen = sm_gen + kOffEpi + (size_t)warp * 2048;
+    const uint32_t my_res_bar = res_bar + 8 * warp;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    auto decode = [&](int tn, int& b, int4& inf) {
+      const int item = (int)blockIdx.x + tn * (int)gridDim.x;
       b = item / nfast;
       inf = __ldg(info + __ldg(flist + (item - b * nfast)));
     };
@@ -697,23 +723,24 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       const int ty = inf.w >> 16, tx = inf.w & 0xffff;
       cx = tx * p.tw, cy = b * p.H + ty * p.th + (32 >> p.tw_shift) * q;
     };
-    // epilogue of one tile: TMEM lanes 32q.., accumulator columns 32g..32g+31 -> affine + residual + ReLU -> the warp's swizzled
-    // 2 KB tile -> TMA store.  Runs one stage into the NEXT tile's gather (double-buffered accumulator).
-    auto epilogue = [&](int item, uint32_t tn) {
+    // epilogue of tile tn: TMEM lanes 32q.., accumulator columns 32eg..32eg+31 -> affine + residual + ReLU -> the warp's swizzled 2 KB
+    // tile -> TMA store.  Called >= 6 stages into the NEXT tile's gather: the A ring is kFStages = 5 deep, so by then every MMA of
+    // tile tn has completed (no wait), and the double-buffered accumulator keeps the tensor pipe busy meanwhile.
+    auto epilogue = [&](int tn) {
       int b;
       int4 inf;
-      decode(item, b, inf);
-      const uint32_t buf = tn & 1;
-      mbar_wait(smem_u32(tfull_bar + buf), (tn >> 1) & 1);
+      decode(tn, b, inf);
+      const uint32_t buf = (uint32_t)tn & 1u;
+      mbar_wait(tfull_bar + 8 * buf, ((uint32_t)tn >> 1) & 1u);
       tc_fence_after();
-      const int c0 = g * 32;
+      const int c0 = eg * 32;
       uint32_t v[32];
-      tmem_ld32(tmem_base + buf * 128u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16), v);
-      if (p.has_res) mbar_wait(smem_u32(res_bar + warp), tn & 1);
+      tmem_ld32(tmem_base + buf * 128u + (uint32_t)c0 + lane_off, v);
+      if (p.has_res) mbar_wait(my_res_bar, (uint32_t)tn & 1u);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (int gg = 0; gg < 4; ++gg) {
-        uint8_t* ep = etile + lane * 64 + ((gg ^ ((lane >> 1) & 3)) << 4);
+        uint8_t* ep = etile_gen + lane * 64 + ((gg ^ ((lane >> 1) & 3)) << 4);
         float y[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[gg * 8 + e]);
@@ -746,126 +773,154 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       if (lane == 0) {
         int cx, cy;
         epi_coords(b, inf, cx, cy);
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_out), "r"(c0), "r"(cx), "r"(cy), "r"(smem_u32(etile))
-                     : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_out), "r"(c0), "r"(cx), "r"(cy), "r"(etile) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty_bar + buf));
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
+    };
+    // this tile's residual piece -> the warp's epilogue tile (free once the previous tile's output store has read it)
+    auto load_residual = [&](int b, const int4& inf) {
+      if (p.has_res && lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        int cx, cy;
+        epi_coords(b, inf, cx, cy);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(my_res_bar), "r"(2048) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(etile), "l"(&tm_res),
+                     "r"(eg * 32), "r"(cx), "r"(cy), "r"(my_res_bar)
+                     : "memory");
+      }
     };
 
-    uint4 v1[2], v2[2], v3[2], v4[2];  // corner values (2 chunks each); loop carried: a skipped load leaves an older finite value, times weight 0
+    uint4 v1[2], v2[2], v3[2], v4[2];  // corner values of one chunk pair; a skipped load leaves an older finite value, times weight 0
 #pragma unroll
     for (int j = 0; j < 2; ++j) v1[j] = v2[j] = v3[j] = v4[j] = make_uint4(0, 0, 0, 0);
-    uint32_t stage = 0, tile_n = 0, slabn = 0;
-    int prev_item = -1;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tile_n) {
-      int b;
-      int4 inf;
-      decode(item, b, inf);
-      const int ty = inf.w >> 16, tx = inf.w & 0xffff, l0 = inf.x, s0 = inf.y;
-      const int pix = (ty * p.th + mr) * p.W + tx * p.tw + mc;  // this thread's pixel inside the image
-      int4 ent = __ldg(p.table + pix);                          // tap 0; later entries are prefetched one stage ahead
-      for (int hf = 0; hf < nhalf; ++hf, ++slabn) {
-        const uint32_t sb = slabn & 1;
-        const uint32_t slab = slab_u32 + sb * kSlabBufBytes;
-        mbar_wait(smem_u32(sfull_bar + sb), (slabn >> 1) & 1);
-        for (int k = 0; k < 9; ++k, ++stage) {
-          const int s = hf * 9 + k;
-          if (s == 1 && prev_item >= 0) epilogue(prev_item, tile_n - 1);
-          if (s == 4 && p.has_res && lane == 0) {
-            // this tile's residual piece -> the warp's epilogue tile (free once the previous tile's output store has read it)
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            int cx, cy;
-            epi_coords(b, inf, cx, cy);
-            const uint32_t bar = smem_u32(res_bar + warp);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048) : "memory");
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(etile)),
-                         "l"(&tm_res), "r"(g * 32), "r"(cx), "r"(cy), "r"(bar)
-                         : "memory");
-          }
-          // slab address of the top-left corner: line (long-axis coordinate - l0, modulo the axis: the grid wraps), then the short axis
-          const int hl = ent.w >> 16, wl = (int)(short)(ent.w & 0xffff);
-          int d = (p.cassini ? hl : wl) - l0;
-          d += d < 0 ? LEN : 0;
-          const int p1 = d * kSlabPitch + ((p.cassini ? wl : hl) - s0);
-          const uint32_t w12 = (uint32_t)ent.y, w34 = (uint32_t)ent.z;
-          const int kn = k == 8 ? 0 : k + 1;
-          if (s + 1 < nst) ent = __ldg(p.table + (size_t)kn * HW + pix);  // next stage's entry, in flight during the loads and the blend
-          {
-            const int pc[4] = {p1, p1 + dW, p1 + dH, p1 + dH + dW};
-            const uint32_t take[4] = {w12 & 0xffffu, w12 >> 16, w34 & 0xffffu, w34 >> 16};
-            uint4* vv[4] = {v1, v2, v3, v4};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              // pixel pc[c] = 128 bytes; its 16-byte chunk cc sits at position cc ^ (pixel & 7) (TMA 128-byte swizzle); chunks 2g and
-              // 2g+1 are the two halves of one 32-byte pair
-              const uint32_t a = slab + (uint32_t)pc[c] * 128u + ((uint32_t)((2 * g) ^ (pc[c] & 7)) << 4);
-              lds_if(vv[c][0], a, take[c]);
-              lds_if(vv[c][1], a ^ 16u, take[c]);
-            }
-          }
-          const uint32_t slot = stage % kFStages, phase = (stage / kFStages) & 1;
-          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);  // the MMAs that read this A slot kFStages stages ago are complete
-          tc_fence_after();
-          uint32_t o[8];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            o[4 * j + 0] = blend2<FMT>(w12, w34, v1[j].x, v2[j].x, v3[j].x, v4[j].x);
-            o[4 * j + 1] = blend2<FMT>(w12, w34, v1[j].y, v2[j].y, v3[j].y, v4[j].y);
-            o[4 * j + 2] = blend2<FMT>(w12, w34, v1[j].z, v2[j].z, v3[j].z, v4[j].z);
-            o[4 * j + 3] = blend2<FMT>(w12, w34, v1[j].w, v2[j].w, v3[j].w, v4[j].w);
-          }
-          // 16 channels of this pixel = 8 packed columns of TMEM lane m, A-operand slot `slot`
-          tmem_st8(tmem_base + kTmemAcc + slot * 32u + (uint32_t)(g * 8) + ((uint32_t)(q * 32) << 16), o);
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(full_bar + slot));
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(sempty_bar + sb));  // every load of this slab has been consumed by a blend
+    const uint32_t total = (uint32_t)my_tiles * (uint32_t)nst;
+    int tn = 0, s = set;                         // (tile, stage in tile) of this warp's current stage
+    if (s >= nst && my_tiles > 0) s -= nst, tn = 1;  // (nst >= 9 > 1: never taken; kept for clarity)
+    int b = 0, l0 = 0, s0 = 0, pix = 0;
+    int4 inf = make_int4(0, 0, 0, 0), ent = make_int4(0, 0, 0, 0);
+    int cur_tn = -1;
+    bool epi_done = true, res_issued = true;
+    for (uint32_t gs = (uint32_t)set; gs < total; gs += 2) {
+      if (tn != cur_tn) {  // first stage of mine in a new tile
+        cur_tn = tn;
+        decode(tn, b, inf);
+        l0 = inf.x, s0 = inf.y;
+        pix = ((inf.w >> 16) * p.th + mr) * p.W + (inf.w & 0xffff) * p.tw + mc;  // this thread's pixel inside the image
+        const int k0 = s >= 9 ? s - 9 : s;
+        ent = __ldg(p.table + (size_t)k0 * HW + pix);
+        epi_done = false, res_issued = false;
       }
-      prev_item = item;
+      const int hf = s >= 9 ? 1 : 0, k = s - 9 * hf;
+      const uint32_t slabn = (uint32_t)(tn * nhalf + hf), sb = slabn & 1u;
+      if (k < 2) mbar_wait(sfull_bar + 8 * sb, (slabn >> 1) & 1u);  // my first stage in this (tile, half): its slab has landed
+      if (!epi_done && s >= 6) {
+        if (tn > 0) epilogue(tn - 1);
+        epi_done = true;
+        if (s + 2 >= nst) load_residual(b, inf), res_issued = true;
+      } else if (epi_done && !res_issued) {
+        load_residual(b, inf), res_issued = true;
+      }
+      // slab address of the top-left corner: line (long-axis coordinate - l0, modulo the axis: the grid wraps), then the short axis
+      const int hl = ent.w >> 16, wl = (int)(short)(ent.w & 0xffff);
+      int d = (CASSINI ? hl : wl) - l0;
+      d += (d >> 31) & LEN;
+      const int p1 = d * kSlabPitch + ((CASSINI ? wl : hl) - s0);
+      const uint32_t w12 = (uint32_t)ent.y, w34 = (uint32_t)ent.z;
+      {  // next stage of mine in this tile: tap k + 2 (mod 9, the following half starts over at tap 0 / 1)
+        const int kn = k + 2 >= 9 ? k + 2 - 9 : k + 2;
+        if (s + 2 < nst) ent = __ldg(p.table + (size_t)kn * HW + pix);
+      }
+      const uint32_t slab = sm + sb * kSlabBufBytes;
+      const int pc[4] = {p1, p1 + dW, p1 + dH, p1 + dH + dW};
+      const uint32_t take[4] = {w12 & 0xffffu, w12 >> 16, w34 & 0xffffu, w34 >> 16};
+      uint32_t ca[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)  // pixel pc = 128 bytes; its 16-byte chunk cc sits at position cc ^ (pixel & 7) (TMA 128-byte swizzle); this is chunk 4g
+        ca[c] = slab + ((uint32_t)pc[c] << 7) + ((uint32_t)(((4 * g) ^ pc[c]) & 7) << 4);
+      const uint32_t slot = gs % kFStages, phase = (gs / kFStages) & 1u;
+      uint32_t o[16];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {  // chunk pairs (4g, 4g+1) and (4g+2, 4g+3): positions ca ^ 0, ^16 and ca ^ 32, ^48
+        lds_if(v1[0], ca[0] ^ (32u * h2), take[0]);
+        lds_if(v1[1], ca[0] ^ (32u * h2 + 16u), take[0]);
+        lds_if(v2[0], ca[1] ^ (32u * h2), take[1]);
+        lds_if(v2[1], ca[1] ^ (32u * h2 + 16u), take[1]);
+        lds_if(v3[0], ca[2] ^ (32u * h2), take[2]);
+        lds_if(v3[1], ca[2] ^ (32u * h2 + 16u), take[2]);
+        lds_if(v4[0], ca[3] ^ (32u * h2), take[3]);
+        lds_if(v4[1], ca[3] ^ (32u * h2 + 16u), take[3]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          o[8 * h2 + 4 * j + 0] = blend2<FMT>(w12, w34, v1[j].x, v2[j].x, v3[j].x, v4[j].x);
+          o[8 * h2 + 4 * j + 1] = blend2<FMT>(w12, w34, v1[j].y, v2[j].y, v3[j].y, v4[j].y);
+          o[8 * h2 + 4 * j + 2] = blend2<FMT>(w12, w34, v1[j].z, v2[j].z, v3[j].z, v4[j].z);
+          o[8 * h2 + 4 * j + 3] = blend2<FMT>(w12, w34, v1[j].w, v2[j].w, v3[j].w, v4[j].w);
+        }
+      }
+      if (k >= 7) {  // my last stage in this (tile, half): every load of the slab has been consumed by a blend
+        __syncwarp();
+        mbar_arrive_lane0(sempty_bar + 8 * sb, lane);
+      }
+      mbar_wait(empty_bar + 8 * slot, phase ^ 1u);  // the MMAs that read this A slot kFStages stages ago are complete
+      tc_fence_after();
+      // 32 channels of this pixel = 16 packed columns of TMEM lane m, A-operand slot `slot`
+      tmem_st16(tmem_base + kTmemAcc + slot * 32u + (uint32_t)(g * 16) + lane_off, o);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive_lane0(full_bar + 8 * slot, lane);
+      s += 2;
+      if (s >= nst) s -= nst, ++tn;
     }
-    if (prev_item >= 0) epilogue(prev_item, tile_n - 1);
+    // drain: the last tile's epilogue (and, for a warp set that never reached stage 6 of it, nothing else is pending)
+    if (my_tiles > 0) {
+      if (!epi_done && my_tiles > 1) epilogue(my_tiles - 2);
+      if (!res_issued) {
+        decode(my_tiles - 1, b, inf);
+        load_residual(b, inf);
+      }
+      epilogue(my_tiles - 1);
+    }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == kGatherWarps + 1) {
     // =================================================== weight loader: one 16 KB bulk copy per stage, up to kFStages ahead
     if (lane == 0) {
-      uint32_t stage = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        for (int s = 0; s < nst; ++s, ++stage) {
-          const int hf = s / 9, k = s - hf * 9;
-          const uint32_t slot = stage % kFStages, phase = (stage / kFStages) & 1;
-          mbar_wait(smem_u32(empty_bar + slot), phase ^ 1);
-          const uint32_t bar = smem_u32(full_bar + slot);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kFBBytes) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(b_s + (size_t)slot * kFBBytes)),
-                       "l"(p.wpk + (size_t)(k * nhalf + hf) * (kFBBytes / 2)), "r"(kFBBytes), "r"(bar)
-                       : "memory");
-        }
+      const uint32_t total = (uint32_t)my_tiles * (uint32_t)nst;
+      int s = 0;
+      for (uint32_t gs = 0; gs < total; ++gs) {
+        const int hf = s >= 9 ? 1 : 0, k = s - 9 * hf;
+        const uint32_t slot = gs % kFStages, phase = (gs / kFStages) & 1u;
+        mbar_wait<true>(empty_bar + 8 * slot, phase ^ 1u);
+        const uint32_t bar = full_bar + 8 * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kFBBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm + kOffB + slot * kFBBytes),
+                     "l"(p.wpk + (size_t)(k * nhalf + hf) * (kFBBytes / 2)), "r"(kFBBytes), "r"(bar)
+                     : "memory");
+        if (++s == nst) s = 0;
       }
     }
   } else if (warp == kGatherWarps + 2) {
     // =================================================== slab loader: one TMA box per line of the long axis, one (tile, half) ahead
     if (lane == 0) {
       uint32_t slabn = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      for (int tn = 0; tn < my_tiles; ++tn) {
+        const int item = (int)blockIdx.x + tn * (int)gridDim.x;
         const int b = item / nfast;
         const int4 inf = __ldg(info + __ldg(flist + (item - b * nfast)));
         const int l0 = inf.x, s0 = inf.y, L = inf.z;
         for (int hf = 0; hf < nhalf; ++hf, ++slabn) {
-          const uint32_t sb = slabn & 1;
-          mbar_wait(smem_u32(sempty_bar + sb), ((slabn >> 1) & 1) ^ 1);
-          const uint32_t bar = smem_u32(sfull_bar + sb);
+          const uint32_t sb = slabn & 1u;
+          mbar_wait<true>(sempty_bar + 8 * sb, ((slabn >> 1) & 1u) ^ 1u);
+          const uint32_t bar = sfull_bar + 8 * sb;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(L * kSlabLineBytes) : "memory");
-          const uint32_t dst0 = smem_u32(slab_s) + sb * kSlabBufBytes;
+          const uint32_t dst0 = sm + sb * kSlabBufBytes;
           for (int l = 0; l < L; ++l) {
             int line = l0 + l;
             line -= line >= LEN ? LEN : 0;  // the sampling grid wraps around the long axis (sphere_conv.py:225)
-            const int cw = p.cassini ? s0 : line, chh = p.cassini ? line : s0;
+            const int cw = CASSINI ? s0 : line, chh = CASSINI ? line : s0;
             asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst0 + l * kSlabPitchBytes),
                          "l"(&tm_x), "r"(hf * 64), "r"(cw), "r"(chh), "r"(b), "r"(bar)
                          : "memory");
@@ -877,23 +932,23 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
     // =================================================== MMA issuer (warp-uniform control flow, one elected lane issues)
     const uint32_t idesc = make_idesc(128, FMT);
     const uint32_t b_hi = desc_hi(128);
-    uint32_t stage = 0, tile_n = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tile_n) {
-      const uint32_t buf = tile_n & 1;
-      mbar_wait(smem_u32(tempty_bar + buf), ((tile_n >> 1) & 1) ^ 1);  // epilogue of tile - 2 has drained this accumulator
+    uint32_t gs = 0;
+    for (int tn = 0; tn < my_tiles; ++tn) {
+      const uint32_t buf = (uint32_t)tn & 1u;
+      mbar_wait(tempty_bar + 8 * buf, (((uint32_t)tn >> 1) & 1u) ^ 1u);  // epilogue of tile - 2 has drained this accumulator
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * 128u;
-      for (int s = 0; s < nst; ++s, ++stage) {
-        const uint32_t slot = stage % kFStages, phase = (stage / kFStages) & 1;
-        mbar_wait(smem_u32(full_bar + slot), phase);
+      for (int s = 0; s < nst; ++s, ++gs) {
+        const uint32_t slot = gs % kFStages, phase = (gs / kFStages) & 1u;
+        mbar_wait(full_bar + 8 * slot, phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a0 = tmem_base + kTmemAcc + slot * 32u;                                  // 64 channels = 32 packed columns
-          const uint32_t b0 = desc_lo(smem_u32(b_s + (size_t)slot * kFBBytes), 128u * 16u);     // [8 chunks][128 rows][16 B]
+          const uint32_t a0 = tmem_base + kTmemAcc + slot * 32u;                     // 64 channels = 32 packed columns
+          const uint32_t b0 = desc_lo(sm + kOffB + slot * kFBBytes, 128u * 16u);   // [8 chunks][128 rows][16 B]
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) umma_ts(tacc, a0 + ks * 8u, b0 + ((uint32_t)(ks * 2 * 128 * 16) >> 4), b_hi, idesc, (s | ks) ? 1u : 0u);
-          umma_commit(smem_u32(empty_bar + slot));
-          if (s == nst - 1) umma_commit(smem_u32(tfull_bar + buf));
+          umma_commit(empty_bar + 8 * slot);
+          if (s == nst - 1) umma_commit(tfull_bar + 8 * buf);
         }
         __syncwarp();
       }
@@ -990,15 +1045,23 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
     static thread_local size_t fattr_dev[kMaxDevices] = {};
     size_t& fattr = fattr_dev[current_device()];
     if (fsmem > fattr) {
-      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_slab_kernel<kFmtBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), "sphere_conv_tc (slab)");
-      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_conv_slab_kernel<kFmtFP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), "sphere_conv_tc (slab)");
+      const void* kernels[4] = {(const void*)sphere_conv_slab_kernel<kFmtBF16, 0>, (const void*)sphere_conv_slab_kernel<kFmtBF16, 1>,
+                                (const void*)sphere_conv_slab_kernel<kFmtFP16, 0>, (const void*)sphere_conv_slab_kernel<kFmtFP16, 1>};
+      for (const void* k : kernels) MODE_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem), "sphere_conv_tc (slab)");
       fattr = fsmem;
     }
     const int fgrid = std::min(B * npos, kNumSMs);
-    if (fmt == kFmtBF16)
-      sphere_conv_slab_kernel<kFmtBF16><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
-    else
-      sphere_conv_slab_kernel<kFmtFP16><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+    if (fmt == kFmtBF16) {
+      if (f.cassini)
+        sphere_conv_slab_kernel<kFmtBF16, 1><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+      else
+        sphere_conv_slab_kernel<kFmtBF16, 0><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+    } else {
+      if (f.cassini)
+        sphere_conv_slab_kernel<kFmtFP16, 1><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+      else
+        sphere_conv_slab_kernel<kFmtFP16, 0><<<fgrid, kFThreads, fsmem, cs>>>(f, tm_x, tm_out, tm_res);
+    }
     MODE_CHECK_LAUNCH("sphere_conv_tc (slab)");
     // the remaining tile positions go through the direct-gather kernel below, in list mode, with the same tile geometry
     p.tw = tw, p.th = th, p.tiles_x = W / tw, p.tiles_y = H / th;

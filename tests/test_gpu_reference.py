@@ -69,7 +69,7 @@ def test_fp32_plan_matches_unmodified_reference_on_gpu(ref_pkg, H, W, D, st, see
   print(f'[ref-gpu] {H}x{W} D={D} {st}: fp32 plan vs unmodified reference: max rel {rel:.2e}, EPE {epe:.2e} px, conf {e_conf:.2e}, same-bin {same_r.float().mean().item():.5f}, '
         f'reference disparity std {spread:.2f} px')
   assert spread > 0.5, 'fixture is saturated'
-  assert rel <= 2e-4 and epe <= 2e-5, (rel, epe)
+  assert rel <= 1e-4 and epe <= 2e-4, (rel, epe)  # north_star: fp32 disparity within 1e-4 relative
   assert same_r.float().mean().item() > 0.999 and e_conf <= 2e-4
 
 
