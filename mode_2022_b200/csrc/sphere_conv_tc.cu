@@ -803,6 +803,7 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
     int4 inf = make_int4(0, 0, 0, 0), ent = make_int4(0, 0, 0, 0);
     int cur_tn = -1;
     bool epi_done = true, res_issued = true;
+    uint32_t pend_bar = 0;                       // full barrier of my previous stage, not yet arrived on
     for (uint32_t gs = (uint32_t)set; gs < total; gs += 2) {
       if (tn != cur_tn) {  // first stage of mine in a new tile
         cur_tn = tn;
@@ -852,6 +853,13 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
         lds_if(v3[1], ca[2] ^ (32u * h2 + 16u), take[2]);
         lds_if(v4[0], ca[3] ^ (32u * h2), take[3]);
         lds_if(v4[1], ca[3] ^ (32u * h2 + 16u), take[3]);
+        if (h2 == 0 && pend_bar != 0) {
+          // publish my PREVIOUS stage: its tcgen05.st has had a whole loop turn-around (and these loads) to complete
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          mbar_arrive_lane0(pend_bar, lane);
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           o[8 * h2 + 4 * j + 0] = blend2<FMT>(w12, w34, v1[j].x, v2[j].x, v3[j].x, v4[j].x);
@@ -866,14 +874,17 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       }
       mbar_wait(empty_bar + 8 * slot, phase ^ 1u);  // the MMAs that read this A slot kFStages stages ago are complete
       tc_fence_after();
-      // 32 channels of this pixel = 16 packed columns of TMEM lane m, A-operand slot `slot`
+      // 32 channels of this pixel = 16 packed columns of TMEM lane m, A-operand slot `slot`; published one stage later (above)
       tmem_st16(tmem_base + kTmemAcc + slot * 32u + (uint32_t)(g * 16) + lane_off, o);
+      pend_bar = full_bar + 8 * slot;
+      s += 2;
+      if (s >= nst) s -= nst, ++tn;
+    }
+    if (pend_bar != 0) {  // publish my last stage
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      mbar_arrive_lane0(full_bar + 8 * slot, lane);
-      s += 2;
-      if (s >= nst) s -= nst, ++tn;
+      mbar_arrive_lane0(pend_bar, lane);
     }
     // drain: the last tile's epilogue (and, for a warp set that never reached stage 6 of it, nothing else is pending)
     if (my_tiles > 0) {
