@@ -438,6 +438,210 @@ def run_reference(args):
   }), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------
+# Other BASELINE.json configs (not the driver's default line): --mode train | twostage | highres
+# ------------------------------------------------------------------------------------------------
+
+
+def _dist_setup():
+  import torch.distributed as dist
+  rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+  local = int(os.environ.get('LOCAL_RANK', 0))
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  return dist, rank, world, local, dev
+
+
+def _timed(dist, world, dev, fn, steps):
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(steps):
+    fn()
+  b.record()
+  torch.cuda.synchronize()
+  ms = torch.tensor([a.elapsed_time(b)], device=dev)
+  if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  return ms.item()
+
+
+def run_train(args):
+  """BASELINE config[2]: stereo-stage TRAINING step, global batch of 8 pairs 1024x512 D=192, camera-pair data-parallel over N GPUs with
+  the bucketed NCCL gradient all-reduce (mode_2022_b200/training.py) overlapped with the backward pass; fp32 like the reference
+  (cuDNN TF32 allowed = torch default).  STRONG scaling: the global batch is fixed, every rank takes 8/N pairs."""
+  dist, rank, world, local, dev = _dist_setup()
+  from mode_2022_b200 import _lib
+  from mode_2022_b200 import training as T
+  from mode_2022_b200.models import ModeDisparity
+  gb = args.pairs or 8
+  if gb % world:
+    raise SystemExit(f'--mode train: global batch {gb} is not divisible by {world} ranks')
+  nb = gb // world
+  torch.manual_seed(0)
+  model = ModeDisparity(MAXDISP, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', precision='fp32').to(dev).train()
+  reducer = T.GradAllReduce(model.parameters())
+  opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))  # reference train_disparity.py:293
+  g = torch.Generator().manual_seed(200 + rank)
+  left_h, right_h = torch.randn(nb, 3, H, W, generator=g).pin_memory(), torch.randn(nb, 3, H, W, generator=g).pin_memory()
+  disp_h = (torch.rand(nb, 1, H, W, generator=g) * (MAXDISP - 1)).pin_memory()
+  mask_h = (torch.rand(nb, 1, H, W, generator=g) < 0.9).pin_memory()
+  left, right, disp, mask = left_h.to(dev), right_h.to(dev), disp_h.to(dev), mask_h.to(dev)
+  loss_box = [None]
+
+  def step():
+    loss_box[0] = T.train_step(model, reducer, opt, left, right, disp, mask)
+
+  def step_e2e():
+    l, r = left_h.to(dev, non_blocking=True), right_h.to(dev, non_blocking=True)
+    d, m = disp_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+    loss_box[0] = T.train_step(model, reducer, opt, l, r, d, m).cpu()
+
+  for _ in range(max(args.warmup, 3)):
+    step()
+  l0 = _lib.launch_count()
+  sampler = ClockSampler(local)
+  sampler.start()
+  ms = _timed(dist, world, dev, step, args.steps)
+  clocks = sampler.stop()
+  launches = _lib.launch_count() - l0
+  ms_e2e = _timed(dist, world, dev, step_e2e, args.steps)
+  # how much of the all-reduce is exposed: time the same step with the collectives skipped (world == 1 semantics) is not available in
+  # a multi-rank run, so report the wait inside finish() instead
+  torch.cuda.synchronize()
+  t0 = time.time()
+  reducer.zero_grad()
+  outs = model(left, right)
+  T.global_masked_loss(outs, disp, mask).backward()
+  torch.cuda.synchronize()
+  t1 = time.time()
+  reducer.finish()
+  torch.cuda.synchronize()
+  t2 = time.time()
+  if rank == 0:
+    print(json.dumps({
+        'metric': 'stereo training pairs/s @512x1024 D=192 (global batch 8)', 'value': round(gb * args.steps / (ms * 1e-3), 3), 'unit': 'pairs/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 2), 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32 (cuDNN TF32 allowed, as the reference trains)', 'data': 'synthetic (randn images, uniform disparities, 90 % mask, seeded random-init weights)',
+        'config': {'workload': f'ModeDisparity training step (3 heads, smooth-L1, Adam), global batch {gb} pairs, Cassini 1024x512, maxdisp=192', 'pairs_per_gpu': nb,
+                   'parallelism': f'camera pairs sharded over {world} GPU(s); bucketed NCCL gradient all-reduce ({reducer.grad_bytes() / 1e6:.1f} MB in {len(reducer.buckets)} buckets) '
+                                  'launched from autograd hooks, overlapped with the backward pass',
+                   'custom_kernels': 'sphere conv fwd+bwd, cost volume fwd+bwd, soft-argmin heads fwd+bwd (libmode_b200); conv2d/conv3d/BN: cuDNN'},
+        'e2e': {'value': round(gb * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(nb * (2 * 3 + 1) * H * W * 4 + nb * H * W),
+                'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_e2e / args.steps, 2)},
+        'gpu_launches': int(launches), 'clocks': clocks, 'loss': float(loss_box[0]),
+        'allreduce': {'bytes': reducer.grad_bytes(), 'buckets': len(reducer.buckets), 'launch_order': reducer.launch_order[:16],
+                      'fwd_bwd_ms': round((t1 - t0) * 1e3, 2), 'exposed_wait_ms_after_backward': round((t2 - t1) * 1e3, 3)},
+        'peak_mem_GB': round(torch.cuda.max_memory_allocated() / 2**30, 1),
+    }), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def run_twostage(args):
+  """BASELINE config[3]: full two-stage MODE.  The 6 camera pairs of a frame are sharded over the ranks (north_star layout), the
+  per-pair disparity / confidence maps are all-gathered (NCCL) into the fusion stage, which warps them into camera 1's frame in
+  memory (StageBoundary: disp->depth, rotation / z-buffer forward warp) and runs ModeFusion.  With N ranks a step processes
+  F = N / gcd(6, N) frames so that every rank holds the same number of pairs; frame f is fused on rank f mod N."""
+  import math as _m
+  dist, rank, world, local, dev = _dist_setup()
+  from mode_2022_b200.models import ModeFusion
+  from mode_2022_b200.sharding import gather_maps, shard_items
+  from mode_2022_b200.utils.geometry import StageBoundary
+  F_ = world // _m.gcd(6, world)
+  n_items = 6 * F_
+  mine = shard_items(n_items, rank, world)
+  model = build_model(dev)
+  fusion = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}, precision='bf16').to(dev).eval()
+  boundary = StageBoundary()
+  g = torch.Generator().manual_seed(300 + rank)
+  left, right = torch.randn(len(mine), 3, H, W, generator=g).to(dev), torch.randn(len(mine), 3, H, W, generator=g).to(dev)
+  rgbs = [torch.randn(1, 3, H, W, generator=g).to(dev) for _ in range(4)]
+  my_frames = [f for f in range(F_) if f % world == rank]
+  out_box = [None]
+
+  def step():
+    with torch.no_grad():
+      pred, conf = model(left, right)
+      both = gather_maps(torch.cat([pred, conf], 1), n_items)  # (6F, 2, H, W) on every rank: the north_star all-gather
+      for f in my_frames:
+        depths, confs = boundary(both[6 * f:6 * f + 6, :1], both[6 * f:6 * f + 6, 1:])
+        out_box[0] = fusion([d.float() for d in depths], [c.float() for c in confs], rgbs)
+
+  for _ in range(max(args.warmup, 3)):
+    step()
+  sampler = ClockSampler(local)
+  sampler.start()
+  ms = _timed(dist, world, dev, step, args.steps)
+  clocks = sampler.stop()
+  # stage shares on rank 0 (CUDA events around each stage of one step)
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+  with torch.no_grad():
+    ev[0].record()
+    pred, conf = model(left, right)
+    ev[1].record()
+    both = gather_maps(torch.cat([pred, conf], 1), n_items)
+    ev[2].record()
+    for f in my_frames:
+      depths, confs = boundary(both[6 * f:6 * f + 6, :1], both[6 * f:6 * f + 6, 1:])
+      fusion([d.float() for d in depths], [c.float() for c in confs], rgbs)
+    ev[3].record()
+  torch.cuda.synchronize()
+  if rank == 0:
+    print(json.dumps({
+        'metric': 'two-stage MODE frames/s @512x1024 D=192 (6 pairs + fusion per frame)', 'value': round(F_ * args.steps / (ms * 1e-3), 3), 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak' if F_ > 1 else 'strong',
+        'vs_baseline': None, 'dtype': PRECISION + ' stereo stage, bf16 autocast ModeFusion', 'data': 'synthetic',
+        'config': {'workload': f'{F_} frame(s)/step: {n_items} camera pairs sharded over {world} GPU(s) -> NCCL all-gather of disp/conf maps ({n_items * 2 * H * W * 4 / 1e6:.0f} MB) -> '
+                               'in-memory stage boundary (disp->depth, rotate / z-buffer warp) -> ModeFusion',
+                   'pairs_per_gpu': len(mine), 'frames_fused_on_rank0': len(my_frames)},
+        'pairs_per_s': round(n_items * args.steps / (ms * 1e-3), 2),
+        'stage_ms_rank0': {'stereo': round(ev[0].elapsed_time(ev[1]), 3), 'all_gather': round(ev[1].elapsed_time(ev[2]), 3),
+                           'boundary_plus_fusion': round(ev[2].elapsed_time(ev[3]), 3)},
+        'clocks': clocks,
+    }), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def run_highres(args):
+  """BASELINE config[4]: 2048x1024 Cassini (= "1024x2048 equirect"), maxdisp=192, one pair per rank per step."""
+  dist, rank, world, local, dev = _dist_setup()
+  from mode_2022_b200 import _lib
+  from mode_2022_b200.models import ModeDisparity
+  Hh, Wh = 2048, 1024
+  nb = args.pairs or 1
+  torch.manual_seed(0)
+  model = ModeDisparity(MAXDISP, conv='Sphere', in_height=Hh, in_width=Wh, sphereType='Cassini', out_conf=True, precision=PRECISION).to(dev).eval()
+  g = torch.Generator().manual_seed(400 + rank)
+  left, right = torch.randn(nb, 3, Hh, Wh, generator=g).to(dev), torch.randn(nb, 3, Hh, Wh, generator=g).to(dev)
+  with torch.no_grad():
+    for _ in range(max(args.warmup, 3)):
+      model(left, right)
+    ms = _timed(dist, world, dev, lambda: model(left, right), args.steps)
+    roof = None
+    if rank == 0:
+      _lib.PROFILE = []
+      for _ in range(2):
+        model(left, right)
+      torch.cuda.synchronize()
+      prof, _lib.PROFILE = _lib.PROFILE, None
+      roof = roofline_report(prof, 2)
+  if rank == 0:
+    print(json.dumps({
+        'metric': 'stereo pairs/s @1024x2048 D=192', 'value': round(nb * world * args.steps / (ms * 1e-3), 2), 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': PRECISION,
+        'data': 'synthetic', 'config': {'workload': f'ModeDisparity stereo stage, {nb} pair(s)/step/GPU, Cassini 2048x1024 (=1024x2048 ERP), maxdisp=192, out_conf'},
+        'roofline': roof, 'peak_mem_GB': round(torch.cuda.max_memory_allocated() / 2**30, 1),
+    }), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -445,9 +649,18 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--no-graph', action='store_true')
+  ap.add_argument('--mode', default='stereo', choices=['stereo', 'train', 'twostage', 'highres'],
+                  help='stereo = BASELINE config[1] (the default line); train = config[2]; twostage = config[3]; highres = config[4]')
+  ap.add_argument('--pairs', type=int, default=0, help='train: global batch (default 8); highres: pairs per step per GPU (default 1)')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)
+  elif args.mode == 'train':
+    run_train(args)
+  elif args.mode == 'twostage':
+    run_twostage(args)
+  elif args.mode == 'highres':
+    run_highres(args)
   else:
     run_ours(args)
 

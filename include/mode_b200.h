@@ -46,6 +46,9 @@ unsigned long long mode_b200_launch_count(void);
  * tensor-core conv3d consumes).  W % 4 == 0 (f32), C % 8 == 0 (16). */
 int mode_cost_volume_f32(const float* ref, const float* tgt, float* cost, int B, int C, int H, int W, int D4, void* stream);
 int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mode_h16* cost, int B, int C, int H, int W, int D4, void* stream);
+/* backward of the fp32 cost volume (training: autograd through the slice assignments of models/mode_disparity.py:104-113):
+ * grad_cost (B,2C,D4,H,W) -> grad_ref, grad_tgt (B,C,H,W), overwritten; a deterministic gather-sum over the D4 shifts. */
+int mode_cost_volume_backward_f32(const float* grad_cost, float* grad_ref, float* grad_tgt, int B, int C, int H, int W, int D4, void* stream);
 
 /* ---- a1. stem convolution of the feature extractor (tcgen05) ------------------------------------
  * replaces sphere_feature_extraction.firstconv[0] = convbn(3, 32, 7, 2, 3, 1) + ReLU (models/submodule.py:155, 15-17, called
@@ -71,6 +74,10 @@ int mode_costvol_conv_fused(const float* ur, const float* ut, const float* scale
  * models/submodule.py:50-57.  cost: (B, D4, H4, W4) fp32 -> pred (B, H, W) [, conf (B, H, W) or NULL].
  * align_corners=True scales; conf = P[r] + P[clamp(r-1)] + P[clamp(r+1)], r = rint(pred). */
 int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4, int H4, int W4, int D, int H, int W, void* stream);
+/* backward of one soft-argmin head (training: reference autograd through models/mode_disparity.py:131-152, three materialised
+ * (B,D,H,W) volumes per head).  grad_pred (B,H,W) -> grad_cost (B,D4,H4,W4), overwritten (zero-filled by the call); the softmax
+ * statistics are recomputed from `cost`, nothing else is saved by the forward.  fp32 atomics (like ATen's upsample backward). */
+int mode_disp_regress_backward(const float* cost, const float* grad_pred, float* grad_cost, int B, int D4, int H4, int W4, int D, int H, int W, void* stream);
 
 /* ---- a2. spherical convolution forward ----------------------------------------------------------
  * replaces sphere_conv_forward_cuda (sphere_conv_cuda.cpp:129-210) = sphere_im2col_gpu_kernel

@@ -18,11 +18,13 @@ _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 SIGNATURES = {
     'mode_cost_volume_f32': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'mode_cost_volume_16': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    'mode_cost_volume_backward_f32': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'mode_conv3d_classifier_tc': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     'mode_costvol_cols': [_vp, _vp, _i, _i, _i, _vp],
     'mode_costvol_conv_fused': [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_stem_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_disp_regress': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_disp_regress_backward': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _i, _vp],

@@ -100,3 +100,41 @@ extern "C" int mode_cost_volume_16(const mode_h16* ref, const mode_h16* tgt, mod
   MODE_CHECK_LAUNCH("cost_volume_16");
   return MODE_OK;
 }
+
+// ---- backward (training): the volume is a set of shifted views, so its gradient is a gather-sum over the D/4 shifts
+//   grad_ref[b,c,h,w]  = sum_{i <= w, i < D4}       g[b, c,     i, h, w]
+//   grad_tgt[b,c,h,w'] = sum_{i < D4, w' + i < W}   g[b, C + c, i, h, w' + i]
+// (reference: autograd through the slice assignments of models/mode_disparity.py:104-113).  One thread per output element, the D/4
+// reads of a warp are coalesced rows of the (B,2C,D4,H,W) gradient; deterministic (no atomics), fixed summation order i = 0..D4-1.
+__global__ void __launch_bounds__(256) cost_volume_bwd_f32_kernel(const float* __restrict__ g, float* __restrict__ gref, float* __restrict__ gtgt, int C, int H, int W,
+                                                                  int D4, long long n) {
+  const size_t plane = (size_t)H * W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(e % W);
+    long long r = e / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int c2 = (int)(r % (2 * C)), b = (int)(r / (2 * C));
+    const float* gp = g + (((size_t)b * 2 * C + c2) * D4) * plane + (size_t)h * W + w;
+    float acc = 0.f;
+    if (c2 < C) {
+      const int imax = min(w, D4 - 1);
+      for (int i = 0; i <= imax; ++i) acc += __ldg(gp + (size_t)i * plane);
+      gref[(((size_t)b * C + c2) * H + h) * W + w] = acc;
+    } else {
+      const int imax = min(D4 - 1, W - 1 - w);
+      for (int i = 0; i <= imax; ++i) acc += __ldg(gp + (size_t)i * plane + i);
+      gtgt[(((size_t)b * C + (c2 - C)) * H + h) * W + w] = acc;
+    }
+  }
+}
+
+extern "C" int mode_cost_volume_backward_f32(const float* grad_cost, float* grad_ref, float* grad_tgt, int B, int C, int H, int W, int D4, void* stream) {
+  MODE_CHECK_ARG(grad_cost && grad_ref && grad_tgt, "cost_volume_backward_f32: null pointer");
+  MODE_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && D4 > 0, "cost_volume_backward_f32: bad shape");
+  const long long n = (long long)B * 2 * C * H * W;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)kNumSMs * 32);
+  cost_volume_bwd_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_cost, grad_ref, grad_tgt, C, H, W, D4, n);
+  MODE_CHECK_LAUNCH("cost_volume_backward_f32");
+  return MODE_OK;
+}

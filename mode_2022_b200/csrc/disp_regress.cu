@@ -119,3 +119,112 @@ extern "C" int mode_disp_regress(const float* cost, float* pred, float* conf, in
   MODE_CHECK_LAUNCH("disp_regress");
   return MODE_OK;
 }
+
+
+// ---- backward (training): d loss / d logits of one soft-argmin head, fused -- the reference back-propagates through three
+// materialised (B,D,H,W) volumes per head (upsample, softmax, the d-weighted sum: models/mode_disparity.py:131-152).  Here a
+// thread owns one full-resolution pixel: it re-evaluates the pixel's D/4 bilinear logits t[], the softmax statistics and the
+// prediction exactly as the forward kernel does, then
+//     d L / d u_d   = g * p_d * (d - pred)                      (soft-argmin through the softmax)
+//     d L / d t[a] += l_a(d) * dL/du_d                           (transpose of the depth lerp; per-thread column in shared memory)
+//     d L / d cost[a, h_j, w_k] += lh_j * lw_k * dL/dt[a]        (transpose of the (h,w) bilinear)
+// The last step first accumulates into a shared-memory tile of the coarse volume covering the block's pixels (a block = up to 256
+// consecutive pixels of ONE image row: 2 coarse rows x <= 66 columns x D/4), then adds the tile to global memory -- 8x fewer global
+// atomics than one per (pixel, plane, corner).  fp32 atomics: summation order varies from run to run, like ATen's own
+// upsample_trilinear3d_backward.
+constexpr int kBwdCols = 72;  // coarse columns a block of 256 pixels can touch (256 * (W4-1)/(W-1) + 2 <= 66) + slack
+
+__global__ void __launch_bounds__(kRegThreads) disp_regress_bwd_kernel(const float* __restrict__ cost, const float* __restrict__ gpred, float* __restrict__ gcost, int D4,
+                                                                       int H4, int W4, int D, int H, int W, float sd, float sh, float sw) {
+  extern __shared__ float bw_s[];
+  float* t_s = bw_s;                                   // [D4][kRegThreads] bilinear logits
+  float* gt_s = bw_s + (size_t)D4 * kRegThreads;       // [D4][kRegThreads] gradient w.r.t. t
+  float* acc = gt_s + (size_t)D4 * kRegThreads;        // [D4][2][kBwdCols] coarse tile
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int w = blockIdx.x * kRegThreads + threadIdx.x;
+  const bool active = w < W;
+  const int wc = active ? w : W - 1;
+  const float hs = sh * h, ws = sw * wc;
+  const int h0 = (int)hs, w0 = (int)ws;
+  const int h1 = h0 + (h0 < H4 - 1), w1 = w0 + (w0 < W4 - 1);
+  const float lh1 = hs - h0, lw1 = ws - w0;
+  const float lh0 = 1.f - lh1, lw0 = 1.f - lw1;
+  const int wbase = (int)(sw * (blockIdx.x * kRegThreads));  // first coarse column of this block (w0 is monotone in w)
+  for (int i = threadIdx.x; i < D4 * 2 * kBwdCols; i += kRegThreads) acc[i] = 0.f;
+  const float* cb = cost + (size_t)b * D4 * H4 * W4;
+  const int o00 = h0 * W4 + w0, o01 = h0 * W4 + w1, o10 = h1 * W4 + w0, o11 = h1 * W4 + w1;
+  float* t = t_s + threadIdx.x;
+  float* gt = gt_s + threadIdx.x;
+  float m = -INFINITY;
+  for (int d4 = 0; d4 < D4; ++d4) {
+    const float* cp = cb + (size_t)d4 * H4 * W4;
+    const float v = lh0 * (lw0 * __ldg(cp + o00) + lw1 * __ldg(cp + o01)) + lh1 * (lw0 * __ldg(cp + o10) + lw1 * __ldg(cp + o11));
+    t[d4 * kRegThreads] = v;
+    gt[d4 * kRegThreads] = 0.f;
+    m = fmaxf(m, v);
+  }
+  float sum = 0.f, wsum = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float ds = sd * d;
+    const int d0 = (int)ds;
+    const int d1 = d0 + (d0 < D4 - 1);
+    const float l1 = ds - d0, l0 = 1.f - l1;
+    const float e = exp_neg(l0 * t[d0 * kRegThreads] + l1 * t[d1 * kRegThreads] - m);
+    sum += e;
+    wsum = fmaf(e, (float)d, wsum);
+  }
+  const float pr = wsum / sum;
+  const float g = active ? __ldg(gpred + ((size_t)b * H + h) * W + wc) / sum : 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float ds = sd * d;
+    const int d0 = (int)ds;
+    const int d1 = d0 + (d0 < D4 - 1);
+    const float l1 = ds - d0, l0 = 1.f - l1;
+    const float e = exp_neg(l0 * t[d0 * kRegThreads] + l1 * t[d1 * kRegThreads] - m);
+    const float gu = g * e * ((float)d - pr);
+    gt[d0 * kRegThreads] += l0 * gu;
+    gt[d1 * kRegThreads] += l1 * gu;
+  }
+  __syncthreads();  // acc is zeroed
+  if (active) {
+    const int c0 = w0 - wbase, c1 = w1 - wbase;
+    const float k00 = lh0 * lw0, k01 = lh0 * lw1, k10 = lh1 * lw0, k11 = lh1 * lw1;
+    for (int d4 = 0; d4 < D4; ++d4) {
+      const float v = gt[d4 * kRegThreads];
+      float* a = acc + (size_t)d4 * 2 * kBwdCols;
+      atomicAdd(a + c0, k00 * v);
+      atomicAdd(a + c1, k01 * v);
+      atomicAdd(a + kBwdCols + c0, k10 * v);
+      atomicAdd(a + kBwdCols + c1, k11 * v);
+    }
+  }
+  __syncthreads();
+  // the tile's two coarse rows are h0 and h1 (uniform over the block: one image row per block); h1 == h0 at the bottom edge
+  float* gb = gcost + (size_t)b * D4 * H4 * W4;
+  const int ncol = min(kBwdCols, W4 - wbase);
+  for (int i = threadIdx.x; i < D4 * 2 * ncol; i += kRegThreads) {
+    const int c = i % ncol, r = (i / ncol) & 1, d4 = i / (2 * ncol);
+    const float v = acc[((size_t)d4 * 2 + r) * kBwdCols + c];
+    if (v != 0.f) atomicAdd(gb + ((size_t)d4 * H4 + (r ? h1 : h0)) * W4 + wbase + c, v);
+  }
+}
+
+extern "C" int mode_disp_regress_backward(const float* cost, const float* grad_pred, float* grad_cost, int B, int D4, int H4, int W4, int D, int H, int W, void* stream) {
+  MODE_CHECK_ARG(cost && grad_pred && grad_cost, "disp_regress_backward: null pointer");
+  MODE_CHECK_ARG(B > 0 && D4 > 0 && H4 > 0 && W4 > 0 && D > 1 && H > 1 && W > 1, "disp_regress_backward: bad shape");
+  MODE_CHECK_ARG(D4 <= 64, "disp_regress_backward: D/4 = %d > 64 not supported", D4);
+  MODE_CHECK_ARG((long long)kRegThreads * (W4 - 1) / (W - 1) + 3 <= kBwdCols, "disp_regress_backward: upsampling factor W/W4 too small for the coarse tile");
+  const float sd = (float)(D4 - 1) / (float)(D - 1), sh = (float)(H4 - 1) / (float)(H - 1), sw = (float)(W4 - 1) / (float)(W - 1);
+  const size_t smem = ((size_t)2 * D4 * kRegThreads + (size_t)D4 * 2 * kBwdCols) * sizeof(float);
+  static thread_local size_t attr_dev[kMaxDevices] = {};
+  size_t& attr = attr_dev[current_device()];
+  if (smem > 48 * 1024 && smem > attr) {
+    MODE_CHECK_CUDA(cudaFuncSetAttribute(disp_regress_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "disp_regress_backward");
+    attr = smem;
+  }
+  MODE_CHECK_CUDA(cudaMemsetAsync(grad_cost, 0, (size_t)B * D4 * H4 * W4 * sizeof(float), (cudaStream_t)stream), "disp_regress_backward");
+  dim3 grid(ceil_div(W, kRegThreads), H, B);
+  disp_regress_bwd_kernel<<<grid, kRegThreads, smem, (cudaStream_t)stream>>>(cost, grad_pred, grad_cost, D4, H4, W4, D, H, W, sd, sh, sw);
+  MODE_CHECK_LAUNCH("disp_regress_backward");
+  return MODE_OK;
+}

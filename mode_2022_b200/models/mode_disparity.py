@@ -148,17 +148,15 @@ class ModeDisparity(nn.Module):
   # -------------------------------------------------------------------------------------------
   def _forward_train(self, left, right):
     """Training graph (reference mode_disparity.py:99-155): batch-stat BatchNorm, three supervised heads, differentiable end
-    to end in fp32.  The spherical layers run libmode_b200's forward AND backward kernels (SphereConvFunction, SURVEY.md
-    section 8 a3); the cost volume is assembled on the device (the reference zero-fills it on the host and uploads it);
-    everything else is the library code the reference trains with (cuDNN conv / BN / softmax through autograd)."""
+    to end in fp32.  libmode_b200 forward AND backward kernels: the spherical layers (SphereConvFunction, SURVEY.md section 8
+    a3), the cost volume and the three soft-argmin heads; the conv2d / conv3d / BatchNorm layers are the library code the
+    reference trains with (cuDNN through autograd)."""
     fl = self.feature_extraction(left.float())
     fr = self.feature_extraction(right.float())
-    B, Cf, H4, W4 = fl.shape
     d4 = self.maxdisp // 4
-    cost = fl.new_zeros((B, 2 * Cf, d4, H4, W4))
-    for i in range(d4):  # integer shifts: cost[:, :C, i, :, i:] = ref[..., i:], cost[:, C:, i, :, i:] = tgt[..., :W-i]
-      cost[:, :Cf, i, :, i:] = fl[:, :, :, i:]
-      cost[:, Cf:, i, :, i:] = fr[:, :, :, :W4 - i]
+    # integer shifts: cost[:, :C, i, :, i:] = ref[..., i:], cost[:, C:, i, :, i:] = tgt[..., :W-i] -- one kernel; its backward is a
+    # deterministic gather-sum over the shifts (mode_cost_volume_backward_f32), registered on the op with torch.library
+    cost = ops.cost_volume(fl.contiguous(), fr.contiguous(), d4)
     cost0 = self.dres0(cost)
     cost0 = self.dres1(cost0) + cost0
     out1, pre1, post1 = self.dres2(cost0, None, None)
@@ -170,9 +168,7 @@ class ModeDisparity(nn.Module):
     cost1 = self.classif1(out1)
     cost2 = self.classif2(out2) + cost1
     cost3 = self.classif3(out3) + cost2
-    disp = torch.arange(self.maxdisp, device=left.device, dtype=torch.float32).view(1, -1, 1, 1)
-    preds = []
-    for c in (cost1, cost2, cost3):
-      c = F.interpolate(c, [self.maxdisp, left.shape[2], left.shape[3]], mode='trilinear', align_corners=True).squeeze(1)
-      preds.append(torch.sum(F.softmax(c, dim=1) * disp, 1, keepdim=True))
+    # the three supervised heads (reference :131-152): trilinear upsample + softmax + soft-argmin fused, forward AND backward
+    # (mode_disp_regress / mode_disp_regress_backward): the reference materialises three (B,D,H,W) volumes per head for autograd
+    preds = [ops.disp_regress(c, self.maxdisp, left.shape[2], left.shape[3])[0] for c in (cost1, cost2, cost3)]
     return tuple(preds)

@@ -112,6 +112,39 @@ def _(ref, tgt, d4):
   return ref.new_empty((B, d4, H, W, 2 * Cc))
 
 
+@torch.library.custom_op('mode_b200::cost_volume_backward', mutates_args=())
+@_device_guard
+def cost_volume_backward(grad_cost: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+  """grad of the fp32 cost volume: (B,2C,D4,H,W) -> (grad_ref, grad_tgt), each (B,C,H,W): gather-sum over the D4 shifts."""
+  grad_cost = _chk(grad_cost, torch.float32, 'cost_volume_backward')
+  if grad_cost.dim() != 5 or grad_cost.shape[1] % 2:
+    raise ValueError('cost_volume_backward: expected a (B,2C,D4,H,W) gradient')
+  B, C2, d4, H, W = grad_cost.shape
+  gr, gt = grad_cost.new_empty((B, C2 // 2, H, W)), grad_cost.new_empty((B, C2 // 2, H, W))
+  _lib.call('mode_cost_volume_backward_f32', _p(grad_cost), _p(gr), _p(gt), B, C2 // 2, H, W, d4, _stream())
+  return gr, gt
+
+
+@cost_volume_backward.register_fake
+def _(grad_cost):
+  B, C2, d4, H, W = grad_cost.shape
+  return grad_cost.new_empty((B, C2 // 2, H, W)), grad_cost.new_empty((B, C2 // 2, H, W))
+
+
+def _cost_volume_setup(ctx, inputs, output):
+  ctx.is_f32 = inputs[0].dtype == torch.float32
+
+
+def _cost_volume_bwd(ctx, grad):
+  if not ctx.is_f32:
+    raise NotImplementedError('cost_volume: only the fp32 (NCHW -> NCDHW) layout is differentiable; the 16-bit plans are inference-only')
+  gr, gt = cost_volume_backward(grad.contiguous())
+  return gr, gt, None
+
+
+torch.library.register_autograd('mode_b200::cost_volume', _cost_volume_bwd, setup_context=_cost_volume_setup)
+
+
 @_device_guard
 def costvol_conv_weights(weight: torch.Tensor, dtype=torch.bfloat16):
   """dres0[0] weight (32, 64, 3, 3, 3) fp32 -> the two (96, 288) GEMM operands of costvol_conv: row kh*32 + c, column
@@ -186,6 +219,47 @@ def _(cost, maxdisp, height, width):
   return cost.new_empty((B, 1, height, width)), cost.new_empty((B, 1, height, width))
 
 
+@torch.library.custom_op('mode_b200::disp_regress_backward', mutates_args=())
+@_device_guard
+def disp_regress_backward(cost: torch.Tensor, grad_pred: torch.Tensor, maxdisp: int) -> torch.Tensor:
+  """d loss / d logits of one soft-argmin head: cost (B,D4,H4,W4) fp32, grad_pred (B,1,H,W) or (B,H,W) -> (B,D4,H4,W4)."""
+  cost = _chk(cost, torch.float32, 'disp_regress_backward')
+  grad_pred = _chk(grad_pred, torch.float32, 'disp_regress_backward')
+  if cost.dim() != 4:
+    raise ValueError('disp_regress_backward: expected a (B,D4,H4,W4) cost tensor')
+  B, D4, H4, W4 = cost.shape
+  H, W = grad_pred.shape[-2:]
+  if grad_pred.numel() != B * H * W:
+    raise ValueError('disp_regress_backward: grad_pred must be (B,1,H,W)')
+  gcost = torch.empty_like(cost)
+  _lib.call('mode_disp_regress_backward', _p(cost), _p(grad_pred), _p(gcost), B, D4, H4, W4, maxdisp, H, W, _stream())
+  return gcost
+
+
+@disp_regress_backward.register_fake
+def _(cost, grad_pred, maxdisp):
+  return torch.empty_like(cost)
+
+
+def _disp_regress_setup(ctx, inputs, output):
+  cost, maxdisp, height, width = inputs
+  ctx.save_for_backward(cost)
+  ctx.maxdisp = maxdisp
+
+
+def _disp_regress_bwd(ctx, grad_pred, grad_conf):
+  """Gradient flows through the disparity only: the confidence is a rounded-index gather (not differentiable w.r.t. the index; the
+  reference computes it in eval mode only, mode_disparity.py:157-183)."""
+  (cost,) = ctx.saved_tensors
+  shape = cost.shape
+  c4 = cost[:, 0] if cost.dim() == 5 else cost
+  g = disp_regress_backward(c4.contiguous(), grad_pred.contiguous(), ctx.maxdisp)
+  return g.reshape(shape), None, None, None
+
+
+torch.library.register_autograd('mode_b200::disp_regress', _disp_regress_bwd, setup_context=_disp_regress_setup)
+
+
 # ------------------------------------------------------------------------------------------------
 # a2. spherical convolution
 # ------------------------------------------------------------------------------------------------
@@ -219,6 +293,37 @@ def sphere_conv_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.Tensor, sc
 @sphere_conv_f32.register_fake
 def _(x, pos, weight, scale, shift, residual, relu):
   return x.new_empty((x.shape[0], weight.shape[0], x.shape[2], x.shape[3]))
+
+
+@torch.library.custom_op('mode_b200::sphere_conv_backward', mutates_args=())
+@_device_guard
+def sphere_conv_backward(x: torch.Tensor, pos: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  """(grad_input, grad_weight, grad_bias) of the plain fp32 spherical conv, as a traceable op (see sphere_conv_backward_f32)."""
+  gi, gw, gb = sphere_conv_backward_f32(x, pos, weight, grad_out, True, True, True)
+  return gi, gw, gb
+
+
+@sphere_conv_backward.register_fake
+def _(x, pos, weight, grad_out):
+  return torch.empty_like(x), torch.empty_like(weight), x.new_empty((weight.shape[0],))
+
+
+def _sphere_f32_setup(ctx, inputs, output):
+  x, pos, weight, scale, shift, residual, relu = inputs
+  ctx.plain = scale is None and residual is None and not relu
+  ctx.has_bias = shift is not None
+  ctx.save_for_backward(x, pos, weight)
+
+
+def _sphere_f32_bwd(ctx, grad_out):
+  if not ctx.plain:
+    raise NotImplementedError('sphere_conv_f32: only the plain form (scale=None, residual=None, relu=False; shift = bias) is differentiable')
+  x, pos, weight = ctx.saved_tensors
+  gi, gw, gb = sphere_conv_backward(x, pos, weight, grad_out.contiguous())
+  return gi, None, gw, None, (gb if ctx.has_bias else None), None, None
+
+
+torch.library.register_autograd('mode_b200::sphere_conv_f32', _sphere_f32_bwd, setup_context=_sphere_f32_setup)
 
 
 @_device_guard

@@ -498,3 +498,52 @@ def test_sphere_conv_tc_full_size_vs_reference_op(ops, C, st, h, w, dtype):
   print(f'sphere_conv_tc {C}->{Co} @{h}x{w} {st} {dtype}: max err vs exact {err.max().item():.2e} (tol {rel:.2e}), vs rounded-column model {e_model:.2e} '
         f'(tol {SPHERE_TC_TOL_MODEL[dtype]:.2e}), polar columns {err[..., :2].max().item():.2e}')
   assert err.max().item() <= rel and e_model <= SPHERE_TC_TOL_MODEL[dtype]
+
+
+# ---------------------------------------------------------------------------- training: backward kernels registered with torch.library
+@pytest.mark.parametrize('shape,d4', [((1, 32, 16, 8), 4), ((2, 8, 8, 16), 16), ((1, 4, 4, 12), 12), ((1, 32, 6, 8), 20)])
+def test_cost_volume_backward_vs_autograd(ops, shape, d4):
+  """Gradient of the fp32 cost volume (gather-sum over the shifts) against autograd through the oracle's slice assignments."""
+  g = torch.Generator().manual_seed(d4)
+  ref, tgt = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+  gout = torch.randn(shape[0], 2 * shape[1], d4, shape[2], shape[3], generator=g)
+  ro, to = ref.double().requires_grad_(), tgt.double().requires_grad_()
+  O.cost_volume(ro, to, d4).backward(gout.double())
+  rc, tc = ref.cuda().requires_grad_(), tgt.cuda().requires_grad_()
+  ops.cost_volume(rc, tc, d4).backward(gout.cuda())
+  assert (rc.grad.cpu().double() - ro.grad).abs().max().item() <= 1e-5 * max(1.0, ro.grad.abs().max().item())
+  assert (tc.grad.cpu().double() - to.grad).abs().max().item() <= 1e-5 * max(1.0, to.grad.abs().max().item())
+
+
+@pytest.mark.parametrize('B,d4,h4,w4', [(2, 4, 16, 8), (1, 8, 8, 16), (1, 16, 12, 100), (2, 48, 8, 4)])
+def test_disp_regress_backward_vs_autograd(ops, B, d4, h4, w4):
+  """Fused soft-argmin head backward against autograd through F.interpolate + softmax + weighted sum (fp64 on CPU)."""
+  g = torch.Generator().manual_seed(d4 + w4)
+  cost = torch.randn(B, 1, d4, h4, w4, generator=g) * 3
+  D, H, W = 4 * d4, 4 * h4, 4 * w4
+  gp = torch.randn(B, 1, H, W, generator=g)
+  co = cost.double().requires_grad_()
+  O.disparity_regression(co, D, H, W).backward(gp.double())
+  cc = cost.cuda().requires_grad_()
+  pred, conf = ops.disp_regress(cc, D, H, W)
+  pred.backward(gp.cuda())
+  assert cc.grad.shape == cost.shape
+  err = (cc.grad.cpu().double() - co.grad).abs().max().item()
+  assert err <= 2e-5 * max(1.0, co.grad.abs().max().item()), err
+  assert (pred.detach().cpu() - O.disparity_regression(cost, D, H, W)).abs().max().item() <= 1e-4 * D
+
+
+def test_registered_ops_pass_opcheck(ops):
+  """torch.library.opcheck: schema, fake (meta) implementations and autograd registration of the differentiable ops."""
+  from torch.library import opcheck
+  g = torch.Generator().manual_seed(1)
+  ref, tgt = torch.randn(1, 8, 8, 8, generator=g).cuda().requires_grad_(), torch.randn(1, 8, 8, 8, generator=g).cuda().requires_grad_()
+  opcheck(torch.ops.mode_b200.cost_volume.default, (ref, tgt, 4))
+  cost = (torch.randn(1, 1, 4, 8, 8, generator=g) * 2).cuda().requires_grad_()
+  opcheck(torch.ops.mode_b200.disp_regress.default, (cost, 16, 32, 32), test_utils=('test_schema', 'test_faketensor', 'test_autograd_registration'))
+  x, wgt, pos = _sphere_case(1, 8, 16, 16, 8, 'Cassini', 2)
+  opcheck(torch.ops.mode_b200.sphere_conv_f32.default, (x.cuda().requires_grad_(), pos.cuda(), wgt.cuda().requires_grad_(), None, None, None, False),
+          test_utils=('test_schema', 'test_faketensor', 'test_autograd_registration'))
+  xb = torch.randn(1, 4, 8, 8, 32, generator=g).half().cuda()
+  wp = ops.conv3d_pack_weights((torch.randn(32, 32, 3, 3, 3, generator=g) / 30).cuda(), 0, torch.float16)
+  opcheck(torch.ops.mode_b200.conv3d_bf16.default, (xb, wp, 32, None, None, None, 0, True, False), test_utils=('test_schema', 'test_faketensor'))
