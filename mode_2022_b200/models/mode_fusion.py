@@ -102,14 +102,18 @@ def _reference_init(module):
       m.bias.data.zero_()
 
 
-def _run(net, precision, *inputs):
-  """fp32: the reference's arithmetic.  bf16 (eval only): channels_last + autocast, i.e. cuDNN's 16-bit tensor-core kernels with
-  fp32 accumulation (the fusion stage is 4 % of a frame's FLOPs and plain library code)."""
+def _run(module, net, precision, *inputs):
+  """fp32: the reference's arithmetic (also the training path).  fp16 / bf16 (eval only): the folded 16-bit plan of
+  models/fusion_plan.py -- channels_last cuDNN tensor-core kernels with fp32 accumulation, BN / bias / ReLU in the conv epilogues,
+  weights folded once and re-folded when they change (the fusion stage is plain library code)."""
   if precision == 'fp32' or net.training:
     return net(*inputs)
-  inputs = [t.contiguous(memory_format=torch.channels_last) for t in inputs]
-  with torch.autocast('cuda', dtype=torch.bfloat16):
-    return net(*inputs).float()
+  key = sum(t._version + t.data_ptr() for t in list(net.parameters()) + list(net.buffers())) & 0xFFFFFFFFFFFF
+  if getattr(module, '_fplan', None) is None or module._fplan_key != key:
+    from .fusion_plan import FusionPlan
+    module._fplan, module._fplan_key = FusionPlan(net, torch.float16 if precision == 'fp16' else torch.bfloat16), key
+  with torch.no_grad():
+    return module._fplan(*inputs)
 
 
 class Baseline(nn.Module):
@@ -120,7 +124,7 @@ class Baseline(nn.Module):
     _reference_init(self)
 
   def forward(self, depthes):
-    return _run(self.feature_extraction, self.precision, torch.cat(depthes, 1))
+    return _run(self, self.feature_extraction, self.precision, torch.cat(depthes, 1))
 
 
 class ModeFusion(nn.Module):
@@ -133,4 +137,4 @@ class ModeFusion(nn.Module):
   def forward(self, depthes, confs, rgbs):
     """depthes/confs: 6 x (B,1,H,W); rgbs: 4 x (B,3,H,W) -> (B,1,H,W) in [0, maxdepth]."""
     pairs = [t for dc in zip(depthes, confs) for t in dc]  # depth0, conf0, depth1, conf1, ...
-    return _run(self.feature_extraction, self.precision, torch.cat(pairs, 1), torch.cat(rgbs, 1))
+    return _run(self, self.feature_extraction, self.precision, torch.cat(pairs, 1), torch.cat(rgbs, 1))

@@ -103,3 +103,54 @@ class HostPipeline:
     k = ticket % self.depth
     self.ev_out[k].synchronize()
     return self.h_pred[k], (self.h_conf[k] if self._with_conf else None)
+
+
+class FusionStage:
+  """Stage 2 of a frame as one replayable unit: the in-memory stage boundary (disparity -> depth, rotation / z-buffer forward warp of
+  the 6 pairs into camera 1's frame; reference save_output_disparity_stage.py:105-160 + the npz/PNG files it replaces) followed by
+  ModeFusion (reference test_fusion.py:67-102), captured in ONE CUDA graph: ~90 small launches (geometry: ~40, fusion: ~50 cuDNN
+  calls) whose launch latency would otherwise be comparable to their run time.
+
+    stage = FusionStage(fusion_model, height=1024, width=512)
+    depth = stage(disp6, conf6, rgbs)      # (6,1,H,W), (6,1,H,W), 4 x (1,3,H,W) device tensors -> (1,1,H,W), valid until the next call
+  """
+
+  def __init__(self, fusion, height: int, width: int, boundary=None, use_graph: bool = True, device=None):
+    from .utils.geometry import StageBoundary
+    if fusion.training:
+      raise RuntimeError('FusionStage runs the inference plan: call fusion.eval() first')
+    self.fusion, self.boundary = fusion, boundary or StageBoundary()
+    self.dev = torch.device(device) if device is not None else next(fusion.parameters()).device
+    self._disp = torch.zeros(6, 1, height, width, device=self.dev)
+    self._conf = torch.zeros(6, 1, height, width, device=self.dev)
+    self._rgbs = [torch.zeros(1, 3, height, width, device=self.dev) for _ in range(4)]
+    self.graph = None
+    with torch.no_grad(), torch.cuda.device(self.dev):
+      self._disp.uniform_(1.0, 100.0)  # a plausible disparity field for the warm-up (all-zero disparities mean depth 1000 everywhere)
+      out = self._run()  # builds the folded plan, the constant grids and warms up cuDNN
+      if use_graph:
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+          self._run()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+          out = self._run()
+      self._out = out
+      torch.cuda.synchronize(self.dev)
+
+  def _run(self):
+    depths, confs = self.boundary(self._disp, self._conf)
+    return self.fusion([d.float() for d in depths], [c.float() for c in confs], self._rgbs)
+
+  def __call__(self, disp6: torch.Tensor, conf6: torch.Tensor, rgbs):
+    with torch.no_grad(), torch.cuda.device(self.dev):
+      self._disp.copy_(disp6)
+      self._conf.copy_(conf6)
+      for dst, src in zip(self._rgbs, rgbs):
+        dst.copy_(src)
+      if self.graph is not None:
+        self.graph.replay()
+        return self._out
+      return self._run()

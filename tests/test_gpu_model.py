@@ -235,7 +235,7 @@ def test_fusion_matches_reference_golden(name):
   shapes = json.load(open(os.path.join(Hh.GOLD, 'mode_fusion_keys.json' if name == 'fusion' else 'baseline_keys.json')))
   depthes, confs, rgbs = Hh.fusion_inputs(64, 32, 4)
   cu = lambda ts: [t.cuda() for t in ts]
-  for precision, tol in (('fp32', 2e-4), ('bf16', 0.15)):
+  for precision, tol in (('fp32', 2e-4), ('fp16', 0.02), ('bf16', 0.15)):
     m = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}, precision=precision) if name == 'fusion' else Baseline(20.0, precision=precision)
     assert {k: list(v.shape) for k, v in m.state_dict().items()} == shapes
     m.load_state_dict(O.synthetic_state_dict(shapes, seed=4))
@@ -301,3 +301,25 @@ def test_ops_follow_the_tensors_device_not_the_current_one():
   assert torch.equal(outs[0], outs[1])
   with pytest.raises(RuntimeError):
     ops.cost_volume(torch.zeros(1, 8, 4, 4, device='cuda:0'), torch.zeros(1, 8, 4, 4, device='cuda:1'), 1)
+
+
+def test_fusion_stage_graph_matches_eager():
+  """pipeline.FusionStage (stage boundary + ModeFusion in one CUDA graph) returns what the eager calls return."""
+  from mode_2022_b200.models import ModeFusion
+  from mode_2022_b200.pipeline import FusionStage
+  from mode_2022_b200.utils.geometry import StageBoundary
+  H, W = 64, 32
+  fusion = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}, precision='fp16').cuda().eval()
+  g = torch.Generator().manual_seed(2)
+  disp = (torch.rand(6, 1, H, W, generator=g) * 60 + 1).cuda()
+  conf = torch.rand(6, 1, H, W, generator=g).cuda()
+  rgbs = [torch.randn(1, 3, H, W, generator=g).cuda() for _ in range(4)]
+  with torch.no_grad():
+    depths, confs = StageBoundary()(disp, conf)
+    want = fusion([d.float() for d in depths], [c.float() for c in confs], rgbs)
+  for use_graph in (True, False):
+    st = FusionStage(fusion, H, W, use_graph=use_graph)
+    got = st(disp, conf, rgbs)
+    assert got.shape == (1, 1, H, W) and torch.equal(got, want)
+    got2 = st(disp * 0.5, conf, rgbs)  # replay with new inputs
+    assert not torch.equal(got2, want)
