@@ -117,9 +117,14 @@ __device__ __forceinline__ void warp_target(T r1, float sp, float cp, float st, 
   double x1, y1, z1;
   back_project(r1, sp, cp, st, ct, x1, y1, z1);
   const double a = x1 - rt.t[0], b = y1 - rt.t[1], c = z1 - rt.t[2];
-  const double X = __dadd_rn(__dadd_rn(__dmul_rn(rt.r[0], a), __dmul_rn(rt.r[1], b)), __dmul_rn(rt.r[2], c));
-  const double Y = __dadd_rn(__dadd_rn(__dmul_rn(rt.r[3], a), __dmul_rn(rt.r[4], b)), __dmul_rn(rt.r[5], c));
-  const double Z = __dadd_rn(__dadd_rn(__dmul_rn(rt.r[6], a), __dmul_rn(rt.r[7], b)), __dmul_rn(rt.r[8], c));
+  // np.matmul(R, X_1 - t) (geometry.py:127) for stacked 3x3 @ 3x1 runs OpenBLAS' FMA micro-kernel: measured on the AVX-512 hosts of this
+  // pool (exact-arithmetic emulation, tools: tests/test_oracle_golden.py::test_numpy_matmul_rounding_model) every row is
+  //     fma(r2, c, fma(r0, a, r1 * b))          -- product of the MIDDLE column first, then two fused multiply-adds.
+  // One ulp in X/Y/Z moves r_2 by an ulp, which decides z-buffer ties between neighbouring source pixels (constant-depth regions),
+  // so the same operation order is used here.
+  const double X = __fma_rn(rt.r[2], c, __fma_rn(rt.r[0], a, __dmul_rn(rt.r[1], b)));
+  const double Y = __fma_rn(rt.r[5], c, __fma_rn(rt.r[3], a, __dmul_rn(rt.r[4], b)));
+  const double Z = __fma_rn(rt.r[8], c, __fma_rn(rt.r[6], a, __dmul_rn(rt.r[7], b)));
   r2 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(X, X), __dmul_rn(Y, Y)), __dmul_rn(Z, Z)));
   const double theta = atan2(Y, Z);
   double q = X / r2;
@@ -156,7 +161,8 @@ __global__ void warp_scatter_kernel(const T* __restrict__ depth, const float* __
     int tgt;
     warp_target(r1, __ldg(sp + w), __ldg(cp + w), __ldg(st + h), __ldg(ct + h), rt, H, W, r2, tgt);
     const float r2f = (float)r2;
-    if (!(r2f < 100000.f)) continue;  // never beats the initial 100000 sentinel (also drops NaN)
+    if (!(r2 < 100000.0)) continue;  // the fp64 candidate never beats the initial 100000 sentinel (also drops NaN); a candidate just
+                                      // below it that ROUNDS to 100000.f still wins, sets the confidence, and is zeroed in the resolve pass
     const uint32_t bits = __float_as_uint(r2f);  // r2 >= 0: unsigned order == float order
     if (PASS == 0) {
       atomicMin(ws + base + tgt, bits);
@@ -176,6 +182,7 @@ __global__ void warp_resolve_kernel(const float* __restrict__ conf, const uint32
     float v = 0.f, c = 0.f;
     if (bits != 0xFFFFFFFFu) {
       v = __uint_as_float(bits);
+      if (v == 100000.f) v = 0.f;  // view_2[view_2 == 100000] = 0 (geometry.py:141), before the clip
       if (v > 1000.f) v = 1000.f;
       uint32_t first = ws[n + i], lastup = ws[2 * n + i];
       uint32_t src = first;

@@ -77,3 +77,21 @@ def fusion_inputs(H, W, seed, B=1):
   confs = [torch.rand(B, 1, H, W, generator=g) for _ in range(6)]
   rgbs = [torch.randn(B, 3, H, W, generator=g) for _ in range(4)]
   return depthes, confs, rgbs
+
+
+def numpy_matmul_is_fma_102(n=40):
+  """Does THIS host's np.matmul evaluate a stacked (3,3) @ (3,1) product as fma(r2, c, fma(r0, a, r1*b)) per row?  (OpenBLAS' FMA
+  micro-kernel on the AVX-512 hosts of this pool does; the forward-warp kernel follows that order, csrc/geometry.cu.)  Checked with
+  exact rational arithmetic on a sample."""
+  from fractions import Fraction
+  rng = np.random.default_rng(12)
+  R = rng.standard_normal((3, 3))
+  X = rng.standard_normal((n, 3, 1)) * 7
+  Y = np.matmul(R, X)[..., 0]
+  fma = lambda a, b, c: float(Fraction(a) * Fraction(b) + Fraction(c))
+  for i in range(n):
+    v = X[i, :, 0]
+    for r in range(3):
+      if fma(R[r, 2], v[2], fma(R[r, 0], v[0], R[r, 1] * v[1])) != Y[i, r]:
+        return False
+  return True

@@ -162,9 +162,10 @@ def test_disp2depth_all_pairs_vs_golden(ops, gold_dir):
     if pair in ('12', '13', '14'):  # triangulation (+ bilinear resample): fp32 rounding of an fp64 expression
       assert np.abs(d - gd).max() <= 1e-6 * max(1.0, np.abs(gd).max()) * 8, pair
       assert np.abs(c - gc).max() <= 1e-6, pair
-    else:  # forward warp: integer targets + z-buffer; allow a handful of rint-boundary flips from libm ulps
+    else:  # forward warp: integer targets + z-buffer (the kernel follows numpy's FMA order of the rigid transform: identical output)
       bad = (np.abs(d - gd) > 1e-4 * np.maximum(1.0, np.abs(gd))) | (np.abs(c - gc) > 1e-6)
-      assert bad.mean() <= 2e-3, (pair, bad.sum())
+      print(f'disp2depth pair {pair}: {int(bad.sum())} of {bad.size} pixels differ from the reference golden')
+      assert bad.sum() == 0 if Hh.numpy_matmul_is_fma_102() else bad.mean() <= 2e-3, (pair, bad.sum())  # exact: integer targets and z-buffer ties included
 
 
 def test_depth_view_trans_bit_exact_on_identical_depth(ops):
@@ -172,14 +173,20 @@ def test_depth_view_trans_bit_exact_on_identical_depth(ops):
   from mode_2022_b200.utils import geometry as G
   rng = np.random.default_rng(3)
   conf = rng.random((64, 32), dtype=np.float32)
-  for depth in (np.full((64, 32), 2.0), rng.random((64, 32)) * 30, np.where(rng.random((64, 32)) < 0.1, 0, rng.random((64, 32)) * 1000)):
+  exact_host = Hh.numpy_matmul_is_fma_102()
+  for depth in (np.full((64, 32), 2.0), rng.random((64, 32)) * 30, np.where(rng.random((64, 32)) < 0.1, 0, rng.random((64, 32)) * 1000),
+                np.where(rng.random((64, 32)) < 0.3, 99999.99999, rng.random((64, 32)) * 2e5)):  # the 100000 sentinel: fp64 below it, fp32 on it
     for dt in (np.float64, np.float32):
       d = depth.astype(dt)
       for pose in [(0, -1, 0, 0.5 * math.pi, 0, 0), (0, 1, 0, 0, 0, 0), (0, -math.sqrt(2) / 2, -math.sqrt(2) / 2, 0.75 * math.pi, 0, 0)]:
         v_o, c_o = O.depth_view_trans_with_conf(d, conf, *pose)
         v, c = G.depthViewTransWithConf(d, conf, *pose)
         mism = (v != v_o) | (c != c_o)
-        assert mism.mean() <= 1e-3, (dt, pose, mism.sum())
+        # exact -- integer targets, depths, confidences, z-buffer ties included -- whenever this host's numpy rounds the rigid
+        # transform the way the kernel does (fma(r2,c, fma(r0,a, r1*b)), the OpenBLAS order on this pool's AVX-512 hosts);
+        # otherwise the reference's own tie-breaks differ from host to host and only the loose bound is meaningful
+        print(f'depth_view_trans {dt.__name__} pose {pose[1]:+.2f},{pose[2]:+.2f}: {int(mism.sum())} mismatching pixels (exact host model: {exact_host})')
+        assert mism.sum() == 0 if exact_host else mism.mean() <= 1e-3, (dt, pose, int(mism.sum()))
 
 
 def test_rotate_and_c2e_numpy_api(ops):

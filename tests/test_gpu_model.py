@@ -140,7 +140,8 @@ def test_two_stage_pipeline_in_memory():
     od, oc = O.disp2depth(dn[i, 0], cn[i, 0], pair)
     gd, gc = depths[i][0, 0].cpu().numpy(), confs[i][0, 0].cpu().numpy()
     bad = (np.abs(gd - od.astype(np.float32)) > 1e-3 * np.maximum(1.0, np.abs(od))) | (np.abs(gc - oc) > 1e-5)
-    assert bad.mean() <= 5e-3, (pair, bad.mean())
+    print(f'stage boundary pair {pair}: {int(bad.sum())} of {bad.size} pixels differ from the oracle')
+    assert bad.sum() == 0 if Hh.numpy_matmul_is_fma_102() else bad.mean() <= 5e-3, (pair, bad.mean())
   fusion = ModeFusion(20.0, [32, 64, 128, 256], {'depth': 12, 'rgb': 12}).cuda().eval()
   rgbs = [torch.randn(1, 3, H, W, device='cuda') for _ in range(4)]
   with torch.no_grad():
