@@ -97,6 +97,13 @@ int mode_sphere_conv_f32(const float* x, const float* pos, const float* w, const
  * may be NULL to skip it (x may be NULL when grad_w is, w when grad_in is). */
 int mode_sphere_conv_backward_f32(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w, float* grad_bias,
                                   int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream);
+/* the same gradients, bit-identical from run to run: every contribution is accumulated in 64-bit fixed point with integer atomics
+ * (order-free) in `workspace` (mode_sphere_conv_backward_workspace_bytes() bytes, 16-byte aligned, caller-allocated, contents
+ * irrelevant), then converted and ADDED into the fp32 gradients.  The reference's col2im uses fp32 atomicAdd and is not reproducible
+ * (sphere_conv_cuda_kernel.cu:341-352). */
+size_t mode_sphere_conv_backward_workspace_bytes(int B, int C, int H, int W, int Co, int Kh, int Kw);
+int mode_sphere_conv_backward_det_f32(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w, float* grad_bias,
+                                      void* workspace, int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream);
 /* tensor-core (tcgen05) variant: x (B,H,W,C) NHWC 16-bit, w_packed from mode_sphere_conv_pack_weights,
  * out (B,H,W,Co) 16-bit, fp32 accumulation.  C % 64 == 0, Co in {64,128,192,256}, 3x3. */
 /* gather table = the sampling grid pre-digested once per resolution and 16-bit format (fmt = MODE_FMT_*): per (tap,

@@ -29,6 +29,7 @@ SIGNATURES = {
     'mode_sphere_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _i, _vp],
     'mode_sphere_conv_backward_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_sphere_conv_backward_det_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_build_table': [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     'mode_conv3d_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_conv3d_pack_weights': [_vp, _vp, _i, _i, _i, _i, _vp],
@@ -40,7 +41,7 @@ SIGNATURES = {
     'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
 }
-OTHER_SYMBOLS = ['mode_sphere_conv_table_bytes', 'mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
+OTHER_SYMBOLS = ['mode_sphere_conv_table_bytes', 'mode_sphere_conv_backward_workspace_bytes', 'mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
 
 PENDING = set()
 _lib = None
@@ -66,6 +67,8 @@ def load() -> C.CDLL:
     lib.mode_conv3d_packed_weight_elems.argtypes = [_i, _i, _i]
     lib.mode_conv3d_packed_weight_elems.restype = C.c_size_t
   lib.mode_sphere_conv_table_bytes.argtypes = [_i, _i, _i, _i]
+  lib.mode_sphere_conv_backward_workspace_bytes.argtypes = [_i] * 7
+  lib.mode_sphere_conv_backward_workspace_bytes.restype = C.c_size_t
   lib.mode_sphere_conv_table_bytes.restype = C.c_size_t
   _lib = lib
   return lib

@@ -13,8 +13,12 @@
 //          exactly those corners.
 //   wgrad: gW[o,c,k] = sum_{b,pix} gout[b,o,pix] * bilinear(x[b,c], pos[k,pix]): 64 x 64 register-tiled GEMM over the pixel
 //          axis whose B operand is gathered on the fly; partial tiles are combined with atomicAdd.
-// Like the reference, both ACCUMULATE into caller-zeroed gradients (sphere_conv.py:62-64) and the scatter uses fp32 atomics
-// (summation order, hence the last bits, is not deterministic -- SURVEY.md section 8c fixture rule 4).
+// Like the reference, both ACCUMULATE into caller-zeroed gradients (sphere_conv.py:62-64).  The reference's col2im scatters with fp32
+// atomicAdd (kernel.cu:341-352): its grad_input changes in the last bits from run to run (SURVEY.md section 8c fixture rule 4).
+// Here the scatter is ORDER-FREE: with a workspace (mode_sphere_conv_backward_det_f32) every contribution is converted to 64-bit
+// fixed point with a power-of-two scale derived from max|grad_out|, max|w|, max|x| (so that no sum can overflow) and added with
+// integer atomics -- integer addition is associative, so the result is bit-identical from run to run whatever the schedule; a
+// last pass converts back and adds into the fp32 gradients.  Without a workspace the fp32-atomic scatter of the reference is used.
 #include "common.cuh"
 using namespace mode;
 
@@ -42,9 +46,55 @@ __device__ __forceinline__ Stencil make_stencil(float h_im, float w_im, int H, i
 
 constexpr int kCPerThread = 32;
 
+// order-free accumulation: v * 2^e (exact in fp32) -> int64 -> integer atomic add
+struct FixScale {
+  float gin, gw, gb;  // power-of-two scales of the three workspaces
+};
+__device__ __forceinline__ void fix_add(long long* p, float v, float scale) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * scale));
+}
+template <bool DET>
+__device__ __forceinline__ void acc_add(float* fp, long long* ip, size_t idx, float v, float scale) {
+  if (DET)
+    fix_add(ip + idx, v, scale);
+  else
+    atomicAdd(fp + idx, v);
+}
+
+// max|grad_out|, max|w|, max|x| -> the three scales (largest power of two that cannot overflow 2^62 for ANY data with those maxima)
+__global__ void sphere_bwd_absmax_kernel(const float* __restrict__ a, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(a + i)));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));  // non-negative floats order like their bit patterns
+}
+__global__ void sphere_bwd_scale_kernel(const unsigned* __restrict__ mx, FixScale* __restrict__ sc, int B, int C, int Co, int KK, int HW) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float mg = fmaxf(__uint_as_float(mx[0]), 1e-30f), mw = fmaxf(__uint_as_float(mx[1]), 1e-30f), mxx = fmaxf(__uint_as_float(mx[2]), 1e-30f);
+  auto pow2_below = [](double bound) {  // 2^floor(log2(2^62 / bound)), clamped to what an fp32 scale can hold
+    int e = 62 - (int)ceil(log2(bound));
+    e = min(max(e, -100), 100);
+    return (float)ldexp(1.0, e);
+  };
+  // |cols| <= Co * max|w| * max|g|; an input pixel receives at most 4 corners x KK taps x (pixels whose stencil hits it): bounded by
+  // the total bilinear weight mass, <= 4 * KK * 16 on any grid MODE builds (a pole pixel is sampled by every pixel of its rows)...
+  // use the safe bound HW (every pixel of the map samples it once per tap with weight <= 1)
+  sc->gin = pow2_below((double)KK * HW * Co * mw * mg * 2.0);
+  sc->gw = pow2_below((double)B * HW * mg * mxx * 2.0);
+  sc->gb = pow2_below((double)B * HW * mg * 2.0);
+}
+// workspace -> fp32 gradient (accumulating, like the reference's caller-zeroed buffers)
+__global__ void sphere_bwd_unfix_kernel(const long long* __restrict__ ws, float* __restrict__ out, long long n, const float* __restrict__ scale) {
+  const double inv = 1.0 / (double)__ldg(scale);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] += (float)((double)ws[i] * inv);
+}
+
 // ---- dgrad: block = 32 pixels x (blockDim.y groups of 32 input channels); per tap the (Co x Cblk) weight slice sits in smem
+template <bool DET>
 __global__ void __launch_bounds__(128) sphere_dgrad_f32_kernel(const float* __restrict__ gout, const float* __restrict__ pos, const float* __restrict__ wgt,
-                                                               float* __restrict__ gin, int C, int H, int W, int Co, int KK) {
+                                                               float* __restrict__ gin, long long* __restrict__ gin_fix, const FixScale* __restrict__ fsc, int C, int H, int W,
+                                                               int Co, int KK) {
   extern __shared__ float ws[];  // [Co][Cblk]
   const int HW = H * W;
   const int Cblk = blockDim.y * kCPerThread;
@@ -56,7 +106,8 @@ __global__ void __launch_bounds__(128) sphere_dgrad_f32_kernel(const float* __re
   const int c0 = threadIdx.y * kCPerThread;
   const int tid = threadIdx.y * 32 + threadIdx.x, nthr = blockDim.y * 32;
   const float* gb = gout + (size_t)b * Co * HW + p;
-  float* gi = gin + (size_t)b * C * HW;
+  const size_t gbase = (size_t)b * C * HW;
+  const float fscale = DET ? fsc->gin : 1.f;
   for (int k = 0; k < KK; ++k) {
     __syncthreads();
     for (int e = tid; e < Co * Cblk; e += nthr) {
@@ -85,11 +136,11 @@ __global__ void __launch_bounds__(128) sphere_dgrad_f32_kernel(const float* __re
     for (int i = 0; i < kCPerThread; ++i) {
       const int c = c_blk0 + c0 + i;
       if (c < C) {
-        float* gc = gi + (size_t)c * HW;
-        if (st.w1 != 0.f) atomicAdd(gc + st.o1, st.w1 * acc[i]);
-        if (st.w2 != 0.f) atomicAdd(gc + st.o2, st.w2 * acc[i]);
-        if (st.w3 != 0.f) atomicAdd(gc + st.o3, st.w3 * acc[i]);
-        if (st.w4 != 0.f) atomicAdd(gc + st.o4, st.w4 * acc[i]);
+        const size_t gc = gbase + (size_t)c * HW;
+        if (st.w1 != 0.f) acc_add<DET>(gin, gin_fix, gc + st.o1, st.w1 * acc[i], fscale);
+        if (st.w2 != 0.f) acc_add<DET>(gin, gin_fix, gc + st.o2, st.w2 * acc[i], fscale);
+        if (st.w3 != 0.f) acc_add<DET>(gin, gin_fix, gc + st.o3, st.w3 * acc[i], fscale);
+        if (st.w4 != 0.f) acc_add<DET>(gin, gin_fix, gc + st.o4, st.w4 * acc[i], fscale);
       }
     }
   }
@@ -97,8 +148,10 @@ __global__ void __launch_bounds__(128) sphere_dgrad_f32_kernel(const float* __re
 
 // ---- wgrad: block = 64 (o) x 64 (c) tile of one tap over one pixel segment; 256 threads x 4x4 accumulators
 constexpr int kWgTile = 64, kWgPix = 32, kWgPad = 68;
+template <bool DET>
 __global__ void __launch_bounds__(256) sphere_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ pos, const float* __restrict__ gout,
-                                                               float* __restrict__ gw, int C, int H, int W, int Co, int KK, int seg_pix, int segs) {
+                                                               float* __restrict__ gw, long long* __restrict__ gw_fix, const FixScale* __restrict__ fsc, int C, int H, int W,
+                                                               int Co, int KK, int seg_pix, int segs) {
   __shared__ __align__(16) float g_s[kWgPix][kWgPad];  // [pixel][o]
   __shared__ __align__(16) float v_s[kWgPix][kWgPad];  // [pixel][c]
   const int HW = H * W;
@@ -158,13 +211,15 @@ __global__ void __launch_bounds__(256) sphere_wgrad_f32_kernel(const float* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = c_blk0 + 4 * tc + j;
-      if (o < Co && c < C) atomicAdd(gw + ((size_t)o * C + c) * KK + k, acc[i][j]);
+      if (o < Co && c < C) acc_add<DET>(gw, gw_fix, ((size_t)o * C + c) * KK + k, acc[i][j], DET ? fsc->gw : 1.f);
     }
   }
 }
 
 // ---- grad_bias[o] += sum_{b,pix} gout[b,o,pix]
-__global__ void __launch_bounds__(256) sphere_bgrad_f32_kernel(const float* __restrict__ gout, float* __restrict__ gbias, int B, int Co, int HW) {
+template <bool DET>
+__global__ void __launch_bounds__(256) sphere_bgrad_f32_kernel(const float* __restrict__ gout, float* __restrict__ gbias, long long* __restrict__ gb_fix,
+                                                               const FixScale* __restrict__ fsc, int B, int Co, int HW) {
   const int o = blockIdx.x;
   float s = 0.f;
   for (int b = blockIdx.y; b < B; b += gridDim.y)
@@ -177,34 +232,60 @@ __global__ void __launch_bounds__(256) sphere_bgrad_f32_kernel(const float* __re
   if (threadIdx.x == 0) {
     float tot = 0.f;
     for (int i = 0; i < 8; ++i) tot += red[i];
-    atomicAdd(gbias + o, tot);
+    acc_add<DET>(gbias, gb_fix, (size_t)o, tot, DET ? fsc->gb : 1.f);
   }
 }
 
 }  // namespace
 
-extern "C" int mode_sphere_conv_backward_f32(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w,
-                                             float* grad_bias, int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream) {
+static int sphere_backward_impl(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w, float* grad_bias,
+                                void* workspace, int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream) {
   MODE_CHECK_ARG(pos && grad_out, "sphere_conv_backward_f32: null pointer");
   MODE_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && Co > 0 && Kh > 0 && Kw > 0, "sphere_conv_backward_f32: bad shape");
   MODE_CHECK_ARG(!grad_in || w, "sphere_conv_backward_f32: grad_in needs the weights");
   MODE_CHECK_ARG(!grad_w || x, "sphere_conv_backward_f32: grad_w needs the input");
   const int KK = Kh * Kw, HW = H * W;
   cudaStream_t s = (cudaStream_t)stream;
+  const bool det = workspace != nullptr;
+  // workspace layout: [FixScale (16 B)][3 x unsigned absmax (16 B)] | int64 grad_in | int64 grad_w | int64 grad_bias
+  const long long n_in = (long long)B * C * HW, n_w = (long long)Co * C * KK;
+  FixScale* fsc = reinterpret_cast<FixScale*>(workspace);
+  unsigned* mx = det ? reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(workspace) + 16) : nullptr;
+  long long* fix_in = det ? reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(workspace) + 32) : nullptr;
+  long long* fix_w = det ? fix_in + (grad_in ? n_in : 0) : nullptr;
+  long long* fix_b = det ? fix_w + (grad_w ? n_w : 0) : nullptr;
+  if (det) {
+    const size_t bytes = 32 + 8 * (size_t)((grad_in ? n_in : 0) + (grad_w ? n_w : 0) + (grad_bias ? Co : 0));
+    MODE_CHECK_CUDA(cudaMemsetAsync(workspace, 0, bytes, s), "sphere_conv_backward_f32");
+    const int nb = kNumSMs * 4;
+    sphere_bwd_absmax_kernel<<<nb, 256, 0, s>>>(grad_out, (long long)B * Co * HW, mx);
+    if (w) sphere_bwd_absmax_kernel<<<nb, 256, 0, s>>>(w, n_w, mx + 1);
+    if (x) sphere_bwd_absmax_kernel<<<nb, 256, 0, s>>>(x, n_in, mx + 2);
+    sphere_bwd_scale_kernel<<<1, 32, 0, s>>>(mx, fsc, B, C, Co, KK, HW);
+    MODE_CHECK_LAUNCH("sphere_conv_backward_f32 (scales)");
+  }
   if (grad_in) {
     const int groups = ceil_div(C, kCPerThread);
     const int by = std::min(groups, 4);
     const size_t smem = (size_t)Co * by * kCPerThread * sizeof(float);
     MODE_CHECK_ARG(smem <= 200 * 1024, "sphere_conv_backward_f32: Co = %d too large", Co);
     static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
-  size_t& attr = attr_dev[current_device()];
+    size_t& attr = attr_dev[current_device()];
     if (smem > 48 * 1024 && smem > attr) {
-      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_dgrad_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_backward_f32");
+      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_dgrad_f32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_backward_f32");
+      MODE_CHECK_CUDA(cudaFuncSetAttribute(sphere_dgrad_f32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sphere_conv_backward_f32");
       attr = smem;
     }
     dim3 grid(ceil_div((long long)HW, 32), ceil_div(groups, by), B), block(32, by);
-    sphere_dgrad_f32_kernel<<<grid, block, smem, s>>>(grad_out, pos, w, grad_in, C, H, W, Co, KK);
+    if (det)
+      sphere_dgrad_f32_kernel<true><<<grid, block, smem, s>>>(grad_out, pos, w, grad_in, fix_in, fsc, C, H, W, Co, KK);
+    else
+      sphere_dgrad_f32_kernel<false><<<grid, block, smem, s>>>(grad_out, pos, w, grad_in, nullptr, nullptr, C, H, W, Co, KK);
     MODE_CHECK_LAUNCH("sphere_conv_backward_f32 (dgrad)");
+    if (det) {
+      sphere_bwd_unfix_kernel<<<kNumSMs * 8, 256, 0, s>>>(fix_in, grad_in, n_in, &fsc->gin);
+      MODE_CHECK_LAUNCH("sphere_conv_backward_f32 (dgrad, fixed point -> fp32)");
+    }
   }
   if (grad_w) {
     // pixel segments: enough blocks to fill the GPU, few enough that the atomic combine stays small
@@ -213,13 +294,40 @@ extern "C" int mode_sphere_conv_backward_f32(const float* x, const float* pos, c
     int seg_pix = ceil_div(ceil_div(HW, segs), kWgPix) * kWgPix;
     segs = ceil_div(HW, seg_pix);
     dim3 grid(B * segs, KK, tiles);
-    sphere_wgrad_f32_kernel<<<grid, 256, 0, s>>>(x, pos, grad_out, grad_w, C, H, W, Co, KK, seg_pix, segs);
+    if (det)
+      sphere_wgrad_f32_kernel<true><<<grid, 256, 0, s>>>(x, pos, grad_out, grad_w, fix_w, fsc, C, H, W, Co, KK, seg_pix, segs);
+    else
+      sphere_wgrad_f32_kernel<false><<<grid, 256, 0, s>>>(x, pos, grad_out, grad_w, nullptr, nullptr, C, H, W, Co, KK, seg_pix, segs);
     MODE_CHECK_LAUNCH("sphere_conv_backward_f32 (wgrad)");
+    if (det) {
+      sphere_bwd_unfix_kernel<<<ceil_div(n_w, 256), 256, 0, s>>>(fix_w, grad_w, n_w, &fsc->gw);
+      MODE_CHECK_LAUNCH("sphere_conv_backward_f32 (wgrad, fixed point -> fp32)");
+    }
   }
   if (grad_bias) {
     dim3 grid(Co, std::min(B, 8));
-    sphere_bgrad_f32_kernel<<<grid, 256, 0, s>>>(grad_out, grad_bias, B, Co, HW);
+    if (det) {
+      sphere_bgrad_f32_kernel<true><<<grid, 256, 0, s>>>(grad_out, grad_bias, fix_b, fsc, B, Co, HW);
+      sphere_bwd_unfix_kernel<<<1, 256, 0, s>>>(fix_b, grad_bias, Co, &fsc->gb);
+    } else {
+      sphere_bgrad_f32_kernel<false><<<grid, 256, 0, s>>>(grad_out, grad_bias, nullptr, nullptr, B, Co, HW);
+    }
     MODE_CHECK_LAUNCH("sphere_conv_backward_f32 (bias)");
   }
   return MODE_OK;
+}
+
+extern "C" int mode_sphere_conv_backward_f32(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w,
+                                             float* grad_bias, int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream) {
+  return sphere_backward_impl(x, pos, w, grad_out, grad_in, grad_w, grad_bias, nullptr, B, C, H, W, Co, Kh, Kw, stream);
+}
+
+extern "C" size_t mode_sphere_conv_backward_workspace_bytes(int B, int C, int H, int W, int Co, int Kh, int Kw) {
+  return 32 + 8 * ((size_t)B * C * H * W + (size_t)Co * C * Kh * Kw + (size_t)Co);
+}
+
+extern "C" int mode_sphere_conv_backward_det_f32(const float* x, const float* pos, const float* w, const float* grad_out, float* grad_in, float* grad_w,
+                                                 float* grad_bias, void* workspace, int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream) {
+  MODE_CHECK_ARG(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sphere_conv_backward_det_f32: needs a 16-byte aligned workspace");
+  return sphere_backward_impl(x, pos, w, grad_out, grad_in, grad_w, grad_bias, workspace, B, C, H, W, Co, Kh, Kw, stream);
 }

@@ -13,6 +13,7 @@ from __future__ import annotations
 import collections
 import ctypes as C
 import functools
+import os
 from typing import Optional
 
 import torch
@@ -341,7 +342,11 @@ def sphere_conv_backward_f32(x: torch.Tensor, pos: torch.Tensor, weight: torch.T
   gi = torch.zeros_like(x) if need_input else None
   gw = torch.zeros_like(weight) if need_weight else None
   gb = torch.zeros(Co, dtype=torch.float32, device=x.device) if need_bias else None
-  _lib.call('mode_sphere_conv_backward_f32', _p(x), _p(pos), _p(weight), _p(grad_out), _p(gi), _p(gw), _p(gb), B, Cc, H, W, Co, Kh, Kw, _stream())
+  if os.environ.get('MODE_B200_NONDETERMINISTIC_BWD'):  # the reference's scheme: fp32 atomicAdd scatter, last bits vary from run to run
+    _lib.call('mode_sphere_conv_backward_f32', _p(x), _p(pos), _p(weight), _p(grad_out), _p(gi), _p(gw), _p(gb), B, Cc, H, W, Co, Kh, Kw, _stream())
+  else:  # default: order-free 64-bit fixed-point accumulation -> bit-identical gradients from run to run
+    ws = torch.empty(_lib.load().mode_sphere_conv_backward_workspace_bytes(B, Cc, H, W, Co, Kh, Kw), dtype=torch.uint8, device=x.device)
+    _lib.call('mode_sphere_conv_backward_det_f32', _p(x), _p(pos), _p(weight), _p(grad_out), _p(gi), _p(gw), _p(gb), _p(ws), B, Cc, H, W, Co, Kh, Kw, _stream())
   return gi, gw, gb
 
 

@@ -554,3 +554,23 @@ def test_registered_ops_pass_opcheck(ops):
   xb = torch.randn(1, 4, 8, 8, 32, generator=g).half().cuda()
   wp = ops.conv3d_pack_weights((torch.randn(32, 32, 3, 3, 3, generator=g) / 30).cuda(), 0, torch.float16)
   opcheck(torch.ops.mode_b200.conv3d_bf16.default, (xb, wp, 32, None, None, None, 0, True, False), test_utils=('test_schema', 'test_faketensor'))
+
+
+def test_sphere_conv_backward_is_run_to_run_deterministic(ops):
+  """The reference's col2im scatters with fp32 atomicAdd (sphere_conv_cuda_kernel.cu:341-352): grad_input differs in the last bits
+  between runs.  The product accumulates in 64-bit fixed point with integer atomics: bit-identical gradients, every run."""
+  x, wgt, pos = _sphere_case(2, 128, 128, 64, 32, 'Cassini', 13)
+  gout = torch.randn(2, 128, 64, 32, generator=torch.Generator().manual_seed(4)) * 1e-4  # tiny gradients: the scale is derived from the data
+  xc, wc, pc, gc = x.cuda(), wgt.cuda(), pos.cuda(), gout.cuda()
+  runs = [ops.sphere_conv_backward_f32(xc, pc, wc, gc, True, True, True) for _ in range(3)]
+  for r in runs[1:]:
+    assert all(torch.equal(a, b) for a, b in zip(runs[0], r))
+  # and it is the same gradient as the fp32-atomic path (up to that path's own summation-order noise)
+  import os
+  os.environ['MODE_B200_NONDETERMINISTIC_BWD'] = '1'
+  try:
+    ref = ops.sphere_conv_backward_f32(xc, pc, wc, gc, True, True, True)
+  finally:
+    del os.environ['MODE_B200_NONDETERMINISTIC_BWD']
+  for a, b in zip(runs[0], ref):
+    assert (a - b).abs().max().item() <= 2e-5 * max(b.abs().max().item(), 1e-12)
