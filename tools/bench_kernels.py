@@ -63,7 +63,7 @@ def main():
     ref, tgt = torch.randn(1, 32, H4, W4, device=dev), torch.randn(1, 32, H4, W4, device=dev)
     ms = timeit(lambda: ops.cost_volume(ref, tgt, D4))
     report('cost_volume_f32', ms, bytes_=2 * ref.numel() * 4 + 64 * D4 * H4 * W4 * 4)
-    rb, tb = ops.nchw_f32_to_nhwc_bf16(ref), ops.nchw_f32_to_nhwc_bf16(tgt)
+    rb, tb = ops.nchw_f32_to_nhwc_bf16(ref, torch.float16), ops.nchw_f32_to_nhwc_bf16(tgt, torch.float16)
     ms = timeit(lambda: ops.cost_volume(rb, tb, D4))
     report('cost_volume_bf16', ms, bytes_=2 * ref.numel() * 2 + 64 * D4 * H4 * W4 * 2)
   if 'regress' in which:
@@ -78,9 +78,9 @@ def main():
     for name, mode, ci, co, dims in layers:
       if only and only not in name:
         continue
-      x = torch.randn(1, *dims, ci, device=dev).bfloat16()
+      x = torch.randn(1, *dims, ci, device=dev).half()
       w = torch.randn((ci, co, 3, 3, 3) if mode == 2 else (co, ci, 3, 3, 3), device=dev) / math.sqrt(27 * ci)
-      wp = ops.conv3d_pack_weights(w, mode)
+      wp = ops.conv3d_pack_weights(w, mode, torch.float16)
       scale, shift = (torch.ones(co, device=dev), torch.zeros(co, device=dev)) if co > 1 else (None, None)
       f32 = co == 1
       ms = timeit(lambda: ops.conv3d_bf16(x, wp, co, scale, shift, None, mode, not f32, f32))
@@ -97,8 +97,8 @@ def main():
     ms = timeit(lambda: ops.sphere_conv_f32(x, pos, w, None, None, None, False), iters=5)
     report('sphere_conv_f32 128->128 @256x128', ms, flops=2 * 128 * 128 * 9 * 256 * 128)
     if hasattr(ops, 'sphere_conv_bf16'):
-      xb = ops.nchw_f32_to_nhwc_bf16(x)
-      wp = ops.sphere_conv_pack_weights(w)
+      xb = ops.nchw_f32_to_nhwc_bf16(x, torch.float16)
+      wp = ops.sphere_conv_pack_weights(w, torch.float16)
       ms = timeit(lambda: ops.sphere_conv_bf16(xb, pos, wp, 128, None, None, None, False))
       report('sphere_conv_bf16 128->128 @256x128', ms, flops=2 * 128 * 128 * 9 * 256 * 128, bytes_=2 * x.numel() * 2 + pos.numel() * 4)
 

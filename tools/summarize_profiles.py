@@ -19,7 +19,7 @@ def short(name):
 
 
 def launch_list():
-  rows = list(csv.reader(l for l in open(os.path.join(OUT, 'launches.csv')) if l.startswith('"')))
+  rows = list(csv.reader(l for l in open(os.path.join(OUT, 'launches.csv' if TAG == 'r01' else f'{TAG}_launches.csv')) if l.startswith('"')))
   h = rows[0]
   ik, im, iv, iid = h.index('Kernel Name'), h.index('Metric Name'), h.index('Metric Value'), h.index('ID')
   iu = h.index('Metric Unit')
@@ -61,7 +61,8 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_active.avg', 'dram__bytes_read.sum
         'lts__t_sector_hit_rate.pct', 'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__warps_active.avg.per_cycle_active']
 
 
 def full(rep, title, out):
@@ -79,20 +80,44 @@ def full(rep, title, out):
   open(os.path.join(PROF, out), 'w').write('\n'.join(lines) + '\n')
 
 
+R02 = [('r02_sphere_slab.ncu-rep', 'sphere_conv_slab_kernel<fp16, cassini> 128->128 @256x128, B=12, residual + ReLU (2688 of 3072 tiles)', 'sphere_conv_slab_ncu.md'),
+       ('r02_sphere_direct.ncu-rep', 'sphere_conv_tc_kernel<fp16,128> in list mode: the 384 polar tiles of the same layer call', 'sphere_conv_direct_polar_ncu.md'),
+       ('r02_conv3d_s1.ncu-rep', 'conv3d_tc_kernel<0,32,fp16,32> 32->32 stride 1 @48x256x128, B=6 (dominant kernel)', 'conv3d_tc_s1_ncu.md'),
+       ('r02_deconv.ncu-rep', 'conv3d_tc_kernel<2,32,fp16,64> transposed 64->32 @24x128x64 -> 48x256x128, B=6, residual + ReLU', 'conv3d_tc_deconv_ncu.md'),
+       ('r02_conv3d_s2small.ncu-rep', 'conv3d_tc_kernel<1,..> 64->64 stride 2 @24x128x64 -> 12x64x32, B=6 (small-grid tail)', 'conv3d_tc_s2_small_ncu.md'),
+       ('r02_cls.ncu-rep', 'conv3d_cls_tc_kernel<fp16> 32->1 classifier, B=6, 48x256x128', 'conv3d_cls_tc_ncu.md'),
+       ('r02_costvol.ncu-rep', 'costvol_conv_kernel<fp16> cost volume fused into dres0[0], B=6, 256x128 features, D/4=48', 'costvol_conv_ncu.md'),
+       ('r02_regress.ncu-rep', 'disp_regress_kernel<48,192> upsample + softmax + soft-argmin + confidence, 1 pair 1024x512', 'disp_regress_ncu.md'),
+       ('r02_cost_volume.ncu-rep', 'cost_volume_bf16_kernel (stand-alone 16-bit NDHWC cost volume), 1 pair', 'cost_volume_ncu.md'),
+       ('r02_stem.ncu-rep', 'stem_conv_tc_kernel<fp16> 3->32 7x7 s2 @1024x512, B=12', 'stem_conv_tc_ncu.md'),
+       ('r02_warp.ncu-rep', 'warp_scatter_kernel (z-buffer forward warp, pass 0), 1024x512', 'geometry_warp_ncu.md'),
+       ('r02_sphere_dgrad.ncu-rep', 'sphere_dgrad_f32_kernel<deterministic> (training, 512x256 D=96 B=2)', 'sphere_dgrad_ncu.md'),
+       ('r02_sphere_wgrad.ncu-rep', 'sphere_wgrad_f32_kernel<deterministic> (training)', 'sphere_wgrad_ncu.md'),
+       ('r02_regress_bwd.ncu-rep', 'disp_regress_bwd_kernel (training: fused soft-argmin head backward)', 'disp_regress_bwd_ncu.md'),
+       ('r02_cost_volume_bwd.ncu-rep', 'cost_volume_bwd_f32_kernel (training: gather-sum over the shifts)', 'cost_volume_bwd_ncu.md')]
+
 if __name__ == '__main__':
   os.makedirs(PROF, exist_ok=True)
   per_launch = launch_list()
-  full('conv3d_s1_b6.ncu-rep', 'conv3d_tc_kernel<0,32,bf16,32> 32->32 stride 1 @48x256x128, B=6 (dominant kernel)', f'{TAG}_conv3d_tc_s1_ncu.md')
-  full('deconv_b6.ncu-rep', 'conv3d_tc_kernel<2,32,bf16,64> transposed 64->32 @24x128x64 -> 48x256x128, B=6, residual + ReLU', f'{TAG}_conv3d_tc_deconv_ncu.md')
-  full('sphere_b12.ncu-rep', 'sphere_conv_tc_kernel<bf16,128> 128->128 @256x128, B=12, residual + ReLU', f'{TAG}_sphere_conv_tc_ncu.md')
-  full('costvol.ncu-rep', 'costvol_conv_kernel<bf16> cost volume fused into dres0[0], B=6, 256x128 features, D/4=48', f'{TAG}_costvol_conv_ncu.md')
-  full('cls.ncu-rep', 'conv3d_cls_tc_kernel<bf16> 32->1 classifier, B=6, 48x256x128', f'{TAG}_conv3d_cls_tc_ncu.md')
-  full('stem.ncu-rep', 'stem_conv_tc_kernel<bf16> 3->32 7x7 s2 @1024x512, B=12', f'{TAG}_stem_conv_tc_ncu.md')
-  for f, o in (('kernel_timings.txt', f'{TAG}_kernel_timings_b1.txt'), ('conv3d_layer_timings_b6.txt', f'{TAG}_layer_timings_b6.txt')):
+  if TAG == 'r01':
+    full('conv3d_s1_b6.ncu-rep', 'conv3d_tc_kernel<0,32,bf16,32> 32->32 stride 1 @48x256x128, B=6 (dominant kernel)', f'{TAG}_conv3d_tc_s1_ncu.md')
+    full('deconv_b6.ncu-rep', 'conv3d_tc_kernel<2,32,bf16,64> transposed 64->32 @24x128x64 -> 48x256x128, B=6, residual + ReLU', f'{TAG}_conv3d_tc_deconv_ncu.md')
+    full('sphere_b12.ncu-rep', 'sphere_conv_tc_kernel<bf16,128> 128->128 @256x128, B=12, residual + ReLU', f'{TAG}_sphere_conv_tc_ncu.md')
+    full('costvol.ncu-rep', 'costvol_conv_kernel<bf16> cost volume fused into dres0[0], B=6, 256x128 features, D/4=48', f'{TAG}_costvol_conv_ncu.md')
+    full('cls.ncu-rep', 'conv3d_cls_tc_kernel<bf16> 32->1 classifier, B=6, 48x256x128', f'{TAG}_conv3d_cls_tc_ncu.md')
+    full('stem.ncu-rep', 'stem_conv_tc_kernel<bf16> 3->32 7x7 s2 @1024x512, B=12', f'{TAG}_stem_conv_tc_ncu.md')
+    files = (('kernel_timings.txt', f'{TAG}_kernel_timings_b1.txt'), ('conv3d_layer_timings_b6.txt', f'{TAG}_layer_timings_b6.txt'))
+    final = 'bench_final.json'
+  else:
+    for rep, title, out in R02:
+      full(rep, title, f'{TAG}_{out}')
+    files = ((f'{TAG}_kernel_timings.txt', f'{TAG}_kernel_timings_b1.txt'), (f'{TAG}_layer_timings_b6.txt', f'{TAG}_layer_timings_b6.txt'))
+    final = f'{TAG}_bench_final.json'
+  for f, o in files:
     if os.path.exists(os.path.join(OUT, f)):
-      keep = [l for l in open(os.path.join(OUT, f)) if l.startswith(('{', 'conv3d_tc', 'sphere_conv_tc', 'pointwise', 'implicit-gemm', 'fused', 'cost_volume +'))]
+      keep = [l for l in open(os.path.join(OUT, f)) if l.startswith(('{', 'conv3d_tc', 'sphere_conv_tc', 'direct-gather', 'pointwise', 'implicit-gemm', 'fused', 'cost_volume +'))]
       open(os.path.join(PROF, o), 'w').write(''.join(keep))
-  if os.path.exists(os.path.join(OUT, 'bench_final.json')):
-    line = [l for l in open(os.path.join(OUT, 'bench_final.json')) if l.startswith('{')][-1]
+  if os.path.exists(os.path.join(OUT, final)):
+    line = [l for l in open(os.path.join(OUT, final)) if l.startswith('{')][-1]
     open(os.path.join(PROF, f'{TAG}_bench_line.json'), 'w').write(line)
   print('conv3d_tc average DRAM MB per launch: %.1f' % per_launch)
