@@ -106,10 +106,12 @@ int mode_sphere_conv_backward_det_f32(const float* x, const float* pos, const fl
                                       void* workspace, int B, int C, int H, int W, int Co, int Kh, int Kw, void* stream);
 /* tensor-core (tcgen05) variant: x (B,H,W,C) NHWC 16-bit, w_packed from mode_sphere_conv_pack_weights,
  * out (B,H,W,Co) 16-bit, fp32 accumulation.  C % 64 == 0, Co in {64,128,192,256}, 3x3. */
-/* gather table = the sampling grid pre-digested once per resolution and 16-bit format (fmt = MODE_FMT_*): per (tap,
- * pixel) the top-left corner's pixel index + the four bilinear weights in that format (0 where the reference's edge rules
- * drop the corner); mode_sphere_conv_table_bytes() bytes, caller-allocated.  The table passed to mode_sphere_conv_tc must
- * have been built with the same fmt. */
+/* gather table = the sampling grid pre-digested once per resolution (independent of the 16-bit format; `fmt` is accepted for ABI
+ * stability): per (tap, pixel) 16 bytes -- the top-left corner's pixel index, the four bilinear weights as fp16 (0 where the
+ * reference's edge rules drop the corner, kernel.cu:97-107,246) and the corner's (row, col) -- followed by the tile classes of the
+ * slab kernel: per 128-pixel tile position the first line / first column / line count of its input neighbourhood, and the lists of
+ * tile positions that fit the shared-memory slab ("fast") or not (polar tile columns: direct-gather kernel).
+ * mode_sphere_conv_table_bytes() bytes, caller-allocated, built once by mode_sphere_conv_build_table (3 small launches). */
 size_t mode_sphere_conv_table_bytes(int H, int W, int Kh, int Kw);
 int mode_sphere_conv_build_table(const float* pos, void* table, int H, int W, int Kh, int Kw, int fmt, void* stream);
 int mode_sphere_conv_tc(const mode_h16* x, const void* table, const mode_h16* w_packed, const float* scale, const float* shift,

@@ -148,7 +148,7 @@ class Bf16Plan(_PlanBase):
         res = ds(y.permute(0, 3, 1, 2), False).permute(0, 2, 3, 1) if ds is not None else y
         y = ops.sphere_conv_bf16(o, pos, w2, c1.out_channels, s2, h2, res.contiguous(), True)
       if all(t.shape[1] % 8 == 0 for t in (raw, reg)) and y.shape[-1] % 8 == 0:
-        # raw / reg are channels_last, i.e. NHWC in memory: stream the three maps into the 320-channel operand of lastconv
+        # raw / reg are channels_last, i.e. NHWC in memory: stream the three maps (64 + 64 + 128) into the 256-channel operand of lastconv
         f = ops.concat3_nhwc(raw.permute(0, 2, 3, 1), reg.permute(0, 2, 3, 1), y).permute(0, 3, 1, 2)
         for c in self.last:
           f = c(f, True)

@@ -39,7 +39,7 @@ def launch_list():
     a[3] += v.get('dram__bytes_write.sum', 0)
   tot = sum(a[1] for a in agg.values())
   lines = [f'# {TAG} -- ncu launch list (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none`,',
-           '# `python bench.py --steps 2 --warmup 1 --no-graph`, first 1200 launches incl. model setup and warm-up)', '',
+           '# `python bench.py --steps 2 --warmup 1 --no-graph`, first launches incl. model setup and warm-up, capped by -c)', '',
            'Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.', '',
            f'total launches captured: {len(per)}; total kernel time {tot:.1f} ms', '', '| kernel | launches | total ms | share | dram read MB / launch | dram write MB / launch |', '|---|---:|---:|---:|---:|---:|']
   for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
