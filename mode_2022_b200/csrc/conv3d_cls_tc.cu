@@ -234,8 +234,11 @@ __global__ void __launch_bounds__(kClsThreads, 2) conv3d_cls_tc_kernel(const Cls
     }
   } else {
     // =========================================================== sum: out[od] = sum over kd of the 9 shifted taps of T(od-1+kd)
-    const int row = (warp - kXW) * 32 + lane;  // output voxel of the tile: (hl, wl)
-    const int hl = row >> 3, wl = row & 7;
+    // output voxel of the tile: sum warp s takes tile rows s, s+4, s+8, s+12 (8 columns each).  A T plane keeps the 18 x 10 halo'd
+    // box with a row pitch of 10 floats: rows 4 apart start 40 floats = 8 banks apart, so the warp's four 8-wide windows fall on 32
+    // distinct banks for every tap -- with four CONSECUTIVE rows (pitch 10) rows 0 and 3 overlapped on 6 banks and every one of the 27
+    // LDS was a 2-way conflict (ncu r02: 44 % of the shared-memory wavefronts of this kernel, LSU pipe 76 %)
+    const int hl = (warp - kXW) + 4 * (lane >> 3), wl = lane & 7;
     uint32_t nbase = 0;  // sequence number of the item's first input plane
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int b, th, tw, o0, o1;
