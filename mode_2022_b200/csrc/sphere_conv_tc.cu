@@ -607,7 +607,10 @@ int make_slab_tmap(CUtensorMap* tm, const void* ptr, int fmt, int B, int C, int 
 // Tiles whose neighbourhood does not fit (polar tile columns: a tap reaches +-128 lines) are left to the direct-gather kernel.
 // =============================================================================================================================
 constexpr int kFStages = 5;                              // ring depth: A slots in TMEM (32 columns each) and weight slabs in smem
-constexpr int kFThreads = (kGatherWarps + 3) * 32;       // 16 gather/epilogue warps, MMA warp, weight loader, slab loader
+constexpr int kFSets = 3;                                // warp sets of the gather role: set j produces the stages j, j + kFSets, ...
+constexpr int kFGatherWarps = 4 * kFSets;                // a set = 4 warps = the 4 TMEM lane quadrants (32 pixels each), 64 channels per thread
+constexpr int kFPieces = 16;                             // epilogue pieces: 4 lane quadrants x 4 groups of 32 output channels, 2 KB each
+constexpr int kFThreads = (kFGatherWarps + 3) * 32;      // gather/epilogue warps, MMA warp, weight loader, slab loader
 constexpr int kFBBytes = 128 * 64 * 2;                   // one weight slab: Co = 128 x 64 channels
 constexpr int kTmemAcc = 256;                            // two 128-column accumulators, then the A ring
 
@@ -632,6 +635,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
                "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+      "%26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+      "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
+      "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
@@ -655,33 +667,33 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
   // 32-bit shared-window arithmetic on `sm`
   const uint32_t sm = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t kOffB = 2 * kSlabBufBytes;                    // weight ring: kFStages x kFBBytes
-  constexpr uint32_t kOffEpi = kOffB + kFStages * kFBBytes;        // kGatherWarps x 2 KB epilogue tiles (32 pixels x 32 channels, 64-byte-swizzled)
-  constexpr uint32_t kOffBar = kOffEpi + kGatherWarps * 2048;
-  const uint32_t full_bar = sm + kOffBar;                          // [kFStages] A slot written (8 warps) + weight slab landed (tx)
+  constexpr uint32_t kOffEpi = kOffB + kFStages * kFBBytes;        // kFPieces x 2 KB epilogue tiles (32 pixels x 32 channels, 64-byte-swizzled)
+  constexpr uint32_t kOffBar = kOffEpi + kFPieces * 2048;
+  const uint32_t full_bar = sm + kOffBar;                          // [kFStages] A slot written (4 warps) + weight slab landed (tx)
   const uint32_t empty_bar = full_bar + 8 * kFStages;              // [kFStages] the MMAs that read the slot have completed
   const uint32_t sfull_bar = empty_bar + 8 * kFStages;             // [2] slab landed (tx)
-  const uint32_t sempty_bar = sfull_bar + 16;                      // [2] slab consumed (16 warps)
+  const uint32_t sempty_bar = sfull_bar + 16;                      // [2] slab consumed (all gather warps)
   const uint32_t tfull_bar = sempty_bar + 16;                      // [2] accumulator complete
-  const uint32_t tempty_bar = tfull_bar + 16;                      // [2] accumulator drained (16 warps)
-  const uint32_t res_bar = tempty_bar + 16;                        // [kGatherWarps] residual piece landed
-  const uint32_t tmem_ptr_u32 = res_bar + 8 * kGatherWarps;
+  const uint32_t tempty_bar = tfull_bar + 16;                      // [2] accumulator drained (all gather warps)
+  const uint32_t res_bar = tempty_bar + 16;                        // [kFPieces] residual piece landed
+  const uint32_t tmem_ptr_u32 = res_bar + 8 * kFPieces;
   uint8_t* const sm_gen = smem_raw + (sm - smem_u32(smem_raw));    // generic pointer to the aligned base
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFStages; ++i) {
-      mbar_init(full_bar + 8 * i, kGatherWarps / 2 + 1);
+      mbar_init(full_bar + 8 * i, 4 + 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(sfull_bar + 8 * i, 1);
-      mbar_init(sempty_bar + 8 * i, kGatherWarps);
+      mbar_init(sempty_bar + 8 * i, kFGatherWarps);
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, kGatherWarps);
+      mbar_init(tempty_bar + 8 * i, kFGatherWarps);
     }
-    for (int i = 0; i < kGatherWarps; ++i) mbar_init(res_bar + 8 * i, 1);
+    for (int i = 0; i < kFPieces; ++i) mbar_init(res_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kGatherWarps) {
+  if (warp == kFGatherWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_u32), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -700,19 +712,17 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
   constexpr int kSlabPitch = slab_pitch(CASSINI != 0), kSlabPitchBytes = kSlabPitch * 128;
   const int my_tiles = (int)blockIdx.x < nitems ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-  if (warp < kGatherWarps) {
+  if (warp < kFGatherWarps) {
     // =================================================== gather producers (+ epilogue)
-    // Gather role: the 16 warps form two sets; set 0 produces the even stages of the CTA's stage sequence, set 1 the odd ones, so a
-    // stage is written by 8 warps = 4 TMEM lane quadrants (32 pixels each) x 2 channel groups (4 chunks = 32 channels = 16 packed
-    // TMEM columns each): per (pixel, tap) ONE table entry, ONE address computation and ONE tcgen05.st serve 32 channels.
-    // Epilogue role: all 16 warps, lane quadrant q x output-channel group eg (32 channels).
-    const int q = warp & 3, g = (warp >> 2) & 1, set = warp >> 3, eg = warp >> 2;
+    // Gather role: kFSets sets of 4 warps; set j produces the stages j, j + kFSets, ... of the CTA's stage sequence.  A thread owns
+    // one PIXEL (TMEM lane) and all 64 channels of the stage: per (pixel, tap) ONE table entry, ONE address computation, 32
+    // predicated LDS.128 (corner x chunk), the blend and ONE tcgen05.st of 32 packed columns.
+    // Epilogue role: all warps; pieces = lane quadrant q x output-channel group eg (32 channels), groups dealt out over the sets.
+    const int q = warp & 3, set = warp >> 2;
+    const int eg0 = set * 4 / kFSets, eg1 = (set + 1) * 4 / kFSets;
     const int m = q * 32 + lane;                 // GEMM row = TMEM lane = pixel of the tile, short image axis fastest
     const int mr = m >> p.tw_shift, mc = m & (p.tw - 1);
     constexpr int dW = CASSINI ? 1 : kSlabPitch, dH = CASSINI ? kSlabPitch : 1;  // slab pixel steps of the (row, col+1) and (row+1, col) corners
-    const uint32_t etile = sm + kOffEpi + (uint32_t)warp * 2048u;
-    uint8_t* const etile_gen = sm_gen + kOffEpi + (size_t)warp * 2048;
-    const uint32_t my_res_bar = res_bar + 8 * warp;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     auto decode = [&](int tn, int& b, int4& inf) {
       const int item = (int)blockIdx.x + tn * (int)gridDim.x;
@@ -723,7 +733,7 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       const int ty = inf.w >> 16, tx = inf.w & 0xffff;
       cx = tx * p.tw, cy = b * p.H + ty * p.th + (32 >> p.tw_shift) * q;
     };
-    // epilogue of tile tn: TMEM lanes 32q.., accumulator columns 32eg..32eg+31 -> affine + residual + ReLU -> the warp's swizzled 2 KB
+    // epilogue of tile tn: TMEM lanes 32q.., accumulator columns 32eg..32eg+31 -> affine + residual + ReLU -> the piece's swizzled 2 KB
     // tile -> TMA store.  Called >= 6 stages into the NEXT tile's gather: the A ring is kFStages = 5 deep, so by then every MMA of
     // tile tn has completed (no wait), and the double-buffered accumulator keeps the tensor pipe busy meanwhile.
     auto epilogue = [&](int tn) {
@@ -733,63 +743,73 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       const uint32_t buf = (uint32_t)tn & 1u;
       mbar_wait(tfull_bar + 8 * buf, ((uint32_t)tn >> 1) & 1u);
       tc_fence_after();
-      const int c0 = eg * 32;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + buf * 128u + (uint32_t)c0 + lane_off, v);
-      if (p.has_res) mbar_wait(my_res_bar, (uint32_t)tn & 1u);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int eg = eg0; eg < eg1; ++eg) {
+        const int piece = eg * 4 + q, c0 = eg * 32;
+        uint8_t* const etile_gen = sm_gen + kOffEpi + (size_t)piece * 2048;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + buf * 128u + (uint32_t)c0 + lane_off, v);
+        if (p.has_res) mbar_wait(res_bar + 8 * piece, (uint32_t)tn & 1u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int gg = 0; gg < 4; ++gg) {
-        uint8_t* ep = etile_gen + lane * 64 + ((gg ^ ((lane >> 1) & 3)) << 4);
-        float y[8];
+        for (int gg = 0; gg < 4; ++gg) {
+          uint8_t* ep = etile_gen + lane * 64 + ((gg ^ ((lane >> 1) & 3)) << 4);
+          float y[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[gg * 8 + e]);
-        if (p.scale) {
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + gg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + gg * 8) + 1);
-          y[0] *= s0.x, y[1] *= s0.y, y[2] *= s0.z, y[3] *= s0.w, y[4] *= s1.x, y[5] *= s1.y, y[6] *= s1.z, y[7] *= s1.w;
-        }
-        if (p.shift) {
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + gg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + gg * 8) + 1);
-          y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
-        }
-        if (p.has_res) {
-          const uint4 r = *reinterpret_cast<const uint4*>(ep);
-          const uint32_t r4[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float r0, r1;
-            unpack2<FMT>(r4[e], r0, r1);
-            y[2 * e] += r0, y[2 * e + 1] += r1;
+          for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[gg * 8 + e]);
+          if (p.scale) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + gg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + gg * 8) + 1);
+            y[0] *= s0.x, y[1] *= s0.y, y[2] *= s0.z, y[3] *= s0.w, y[4] *= s1.x, y[5] *= s1.y, y[6] *= s1.z, y[7] *= s1.w;
           }
-        }
-        if (p.relu) {
+          if (p.shift) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + gg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + gg * 8) + 1);
+            y[0] += s0.x, y[1] += s0.y, y[2] += s0.z, y[3] += s0.w, y[4] += s1.x, y[5] += s1.y, y[6] += s1.z, y[7] += s1.w;
+          }
+          if (p.has_res) {
+            const uint4 r = *reinterpret_cast<const uint4*>(ep);
+            const uint32_t r4[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+            for (int e = 0; e < 4; ++e) {
+              float r0, r1;
+              unpack2<FMT>(r4[e], r0, r1);
+              y[2 * e] += r0, y[2 * e + 1] += r1;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+          }
+          *reinterpret_cast<uint4*>(ep) = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
         }
-        *reinterpret_cast<uint4*>(ep) = make_uint4(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]), pack2<FMT>(y[4], y[5]), pack2<FMT>(y[6], y[7]));
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         int cx, cy;
         epi_coords(b, inf, cx, cy);
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_out), "r"(c0), "r"(cx), "r"(cy), "r"(etile) : "memory");
+        for (int eg = eg0; eg < eg1; ++eg)
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tm_out), "r"(eg * 32), "r"(cx), "r"(cy),
+                       "r"(sm + kOffEpi + (uint32_t)(eg * 4 + q) * 2048u)
+                       : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);
     };
-    // this tile's residual piece -> the warp's epilogue tile (free once the previous tile's output store has read it)
+    // this tile's residual pieces -> the warp's epilogue tiles (free once the previous tile's output stores have read them)
     auto load_residual = [&](int b, const int4& inf) {
       if (p.has_res && lane == 0) {
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         int cx, cy;
         epi_coords(b, inf, cx, cy);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(my_res_bar), "r"(2048) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(etile), "l"(&tm_res),
-                     "r"(eg * 32), "r"(cx), "r"(cy), "r"(my_res_bar)
-                     : "memory");
+        for (int eg = eg0; eg < eg1; ++eg) {
+          const uint32_t bar = res_bar + 8 * (eg * 4 + q);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048) : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                           sm + kOffEpi + (uint32_t)(eg * 4 + q) * 2048u),
+                       "l"(&tm_res), "r"(eg * 32), "r"(cx), "r"(cy), "r"(bar)
+                       : "memory");
+        }
       }
     };
 
@@ -797,14 +817,14 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
 #pragma unroll
     for (int j = 0; j < 2; ++j) v1[j] = v2[j] = v3[j] = v4[j] = make_uint4(0, 0, 0, 0);
     const uint32_t total = (uint32_t)my_tiles * (uint32_t)nst;
-    int tn = 0, s = set;                         // (tile, stage in tile) of this warp's current stage
-    if (s >= nst && my_tiles > 0) s -= nst, tn = 1;  // (nst >= 9 > 1: never taken; kept for clarity)
+    int tn = 0, s = set;                         // (tile, stage in tile) of this warp's current stage (nst >= 9 > kFSets)
     int b = 0, l0 = 0, s0 = 0, pix = 0;
     int4 inf = make_int4(0, 0, 0, 0), ent = make_int4(0, 0, 0, 0);
     int cur_tn = -1;
     bool epi_done = true, res_issued = true;
     uint32_t pend_bar = 0;                       // full barrier of my previous stage, not yet arrived on
-    for (uint32_t gs = (uint32_t)set; gs < total; gs += 2) {
+    uint32_t slot = (uint32_t)set, phase = 0;    // A ring slot / parity of stage gs (gs % kFStages, (gs / kFStages) & 1), kept incrementally
+    for (uint32_t gs = (uint32_t)set; gs < total; gs += kFSets) {
       if (tn != cur_tn) {  // first stage of mine in a new tile
         cur_tn = tn;
         decode(tn, b, inf);
@@ -816,11 +836,11 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       }
       const int hf = s >= 9 ? 1 : 0, k = s - 9 * hf;
       const uint32_t slabn = (uint32_t)(tn * nhalf + hf), sb = slabn & 1u;
-      if (k < 2) mbar_wait(sfull_bar + 8 * sb, (slabn >> 1) & 1u);  // my first stage in this (tile, half): its slab has landed
+      if (k < kFSets) mbar_wait(sfull_bar + 8 * sb, (slabn >> 1) & 1u);  // my first stage in this (tile, half): its slab has landed
       if (!epi_done && s >= 6) {
         if (tn > 0) epilogue(tn - 1);
         epi_done = true;
-        if (s + 2 >= nst) load_residual(b, inf), res_issued = true;
+        if (s + kFSets >= nst) load_residual(b, inf), res_issued = true;
       } else if (epi_done && !res_issued) {
         load_residual(b, inf), res_issued = true;
       }
@@ -830,21 +850,20 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       d += (d >> 31) & LEN;
       const int p1 = d * kSlabPitch + ((CASSINI ? wl : hl) - s0);
       const uint32_t w12 = (uint32_t)ent.y, w34 = (uint32_t)ent.z;
-      {  // next stage of mine in this tile: tap k + 2 (mod 9, the following half starts over at tap 0 / 1)
-        const int kn = k + 2 >= 9 ? k + 2 - 9 : k + 2;
-        if (s + 2 < nst) ent = __ldg(p.table + (size_t)kn * HW + pix);
+      {  // next stage of mine in this tile: tap k + kFSets (mod 9: the following half starts over)
+        const int kn = k + kFSets >= 9 ? k + kFSets - 9 : k + kFSets;
+        if (s + kFSets < nst) ent = __ldg(p.table + (size_t)kn * HW + pix);
       }
       const uint32_t slab = sm + sb * kSlabBufBytes;
       const int pc[4] = {p1, p1 + dW, p1 + dH, p1 + dH + dW};
       const uint32_t take[4] = {w12 & 0xffffu, w12 >> 16, w34 & 0xffffu, w34 >> 16};
       uint32_t ca[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)  // pixel pc = 128 bytes; its 16-byte chunk cc sits at position cc ^ (pixel & 7) (TMA 128-byte swizzle); this is chunk 4g
-        ca[c] = slab + ((uint32_t)pc[c] << 7) + ((uint32_t)(((4 * g) ^ pc[c]) & 7) << 4);
-      const uint32_t slot = gs % kFStages, phase = (gs / kFStages) & 1u;
-      uint32_t o[16];
+      for (int c = 0; c < 4; ++c)  // pixel pc = 128 bytes; its 16-byte chunk cc sits at position cc ^ (pixel & 7) (TMA 128-byte swizzle); this is chunk 0
+        ca[c] = slab + ((uint32_t)pc[c] << 7) + ((uint32_t)(pc[c] & 7) << 4);
+      uint32_t o[32];
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {  // chunk pairs (4g, 4g+1) and (4g+2, 4g+3): positions ca ^ 0, ^16 and ca ^ 32, ^48
+      for (int h2 = 0; h2 < 4; ++h2) {  // chunk pairs (2 h2, 2 h2 + 1): positions ca ^ 32 h2, ca ^ (32 h2 + 16)
         lds_if(v1[0], ca[0] ^ (32u * h2), take[0]);
         lds_if(v1[1], ca[0] ^ (32u * h2 + 16u), take[0]);
         lds_if(v2[0], ca[1] ^ (32u * h2), take[1]);
@@ -868,16 +887,18 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
           o[8 * h2 + 4 * j + 3] = blend2<FMT>(w12, w34, v1[j].w, v2[j].w, v3[j].w, v4[j].w);
         }
       }
-      if (k >= 7) {  // my last stage in this (tile, half): every load of the slab has been consumed by a blend
+      if (k >= 9 - kFSets) {  // my last stage in this (tile, half): every load of the slab has been consumed by a blend
         __syncwarp();
         mbar_arrive_lane0(sempty_bar + 8 * sb, lane);
       }
       mbar_wait(empty_bar + 8 * slot, phase ^ 1u);  // the MMAs that read this A slot kFStages stages ago are complete
       tc_fence_after();
-      // 32 channels of this pixel = 16 packed columns of TMEM lane m, A-operand slot `slot`; published one stage later (above)
-      tmem_st16(tmem_base + kTmemAcc + slot * 32u + (uint32_t)(g * 16) + lane_off, o);
+      // 64 channels of this pixel = 32 packed columns of TMEM lane m, A-operand slot `slot`; published one stage later (above)
+      tmem_st32(tmem_base + kTmemAcc + slot * 32u + lane_off, o);
       pend_bar = full_bar + 8 * slot;
-      s += 2;
+      slot += kFSets;
+      if (slot >= kFStages) slot -= kFStages, phase ^= 1u;
+      s += kFSets;
       if (s >= nst) s -= nst, ++tn;
     }
     if (pend_bar != 0) {  // publish my last stage
@@ -886,7 +907,7 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       __syncwarp();
       mbar_arrive_lane0(pend_bar, lane);
     }
-    // drain: the last tile's epilogue (and, for a warp set that never reached stage 6 of it, nothing else is pending)
+    // drain: the last tile's epilogue (and, for a warp set that never reached stage 6 of it, the one before)
     if (my_tiles > 0) {
       if (!epi_done && my_tiles > 1) epilogue(my_tiles - 2);
       if (!res_issued) {
@@ -896,7 +917,7 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
       epilogue(my_tiles - 1);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  } else if (warp == kGatherWarps + 1) {
+  } else if (warp == kFGatherWarps + 1) {
     // =================================================== weight loader: one 16 KB bulk copy per stage, up to kFStages ahead
     if (lane == 0) {
       const uint32_t total = (uint32_t)my_tiles * (uint32_t)nst;
@@ -913,7 +934,7 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
         if (++s == nst) s = 0;
       }
     }
-  } else if (warp == kGatherWarps + 2) {
+  } else if (warp == kFGatherWarps + 2) {
     // =================================================== slab loader: one TMA box per line of the long axis, one (tile, half) ahead
     if (lane == 0) {
       uint32_t slabn = 0;
@@ -967,7 +988,7 @@ __global__ void __launch_bounds__(kFThreads, 1) sphere_conv_slab_kernel(const Fc
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  if (warp == kFGatherWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 }  // namespace
@@ -1052,7 +1073,7 @@ extern "C" int mode_sphere_conv_tc(const mode_h16* x, const void* table, const m
     f.table = (const int4*)table, f.hdr = hdr, f.wpk = w_packed, f.scale = scale, f.shift = shift;
     f.has_res = residual != nullptr, f.relu = relu, f.B = B, f.C = C, f.H = H, f.W = W, f.npos = npos;
     f.th = th, f.tw = tw, f.tw_shift = tw == 8 ? 3 : 4, f.cassini = th > tw;
-    const size_t fsmem = 1024 + 2 * (size_t)kSlabBufBytes + (size_t)kFStages * kFBBytes + kGatherWarps * 2048 + (2 * kFStages + 8 + kGatherWarps) * 8 + 16;
+    const size_t fsmem = 1024 + 2 * (size_t)kSlabBufBytes + (size_t)kFStages * kFBBytes + kFPieces * 2048 + (2 * kFStages + 8 + kFPieces) * 8 + 16;
     static thread_local size_t fattr_dev[kMaxDevices] = {};
     size_t& fattr = fattr_dev[current_device()];
     if (fsmem > fattr) {
