@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libmode_b200.so')
+LIB_PATH = os.environ.get('MODE_B200_LIB') or os.path.join(_HERE, 'lib', 'libmode_b200.so')  # override: kernel experiments (tools/build_variant.sh)
 
 _vp, _i, _f = C.c_void_p, C.c_int, C.c_float
 

@@ -9,11 +9,13 @@
 // channel the 27 taps can be applied BEFORE the spatial shift:
 //     T[v][tap] = sum_c x[v][c] * w[c][tap]                 one GEMM per input voxel, M = voxels, N = 27 (padded to 32), K = 32
 //     out[d,h,w] = sum_{kd,kh,kw} T[(d-1+kd, h-1+kh, w-1+kw)][(kd,kh,kw)]
-// i.e. 4 MMAs (2 M tiles x 2 K steps, N = 32) per halo'd 18 x 10 input plane instead of 18, and a 27-term sum per output voxel
-// out of shared memory.  A CTA walks a 16 x 8 tile column along depth: TMA box (zero-filled halo) -> 4 MMAs -> T in TMEM ->
-// 4 EXTRACT warps spill T into a 3-plane shared-memory ring ([tap][voxel], conflict-free) -> 4 SUM warps emit one output
-// plane per input plane (27 LDS + adds, fp32 residual, coalesced fp32 stores).  Output plane od consumes T(od-1) first and
-// releases its ring slot before touching T(od), T(od+1), so the extraction of plane od+2 overlaps two thirds of the sum.
+// i.e. 4 MMAs (2 M tiles x 2 K steps, N = 32) per halo'd 18 x 10 input plane instead of 18.  The depth part of the sum involves no
+// spatial shift -- S(od)[v][kh,kw] = T(od-1)[v][0,kh,kw] + T(od)[v][1,kh,kw] + T(od+1)[v][2,kh,kw] for the SAME input voxel v -- so
+// the 4 EXTRACT warps (TMEM lane = voxel) carry it in registers across consecutive planes and spill only the 9 completed values per
+// voxel into a shared-memory ring ([kh,kw][voxel], conflict-free); the 4 SUM warps add the 9 spatially shifted values per output
+// voxel (+ fp32 residual, coalesced fp32 stores).  A CTA walks a 16 x 8 tile column along depth: TMA box (zero-filled halo) ->
+// 4 MMAs -> T in TMEM -> extract -> sum.  (First version: all 27 taps went through shared memory -- 27 STS + 27 LDS per voxel and
+// plane; the kernel sat at 0.49 of the HBM bound with the shared-memory port 76 % busy.)
 #include <cuda.h>
 #include <string.h>
 
@@ -27,9 +29,10 @@ constexpr int kClsThreads = (kXW + kSW + 2) * 32;  // + MMA warp, TMA producer
 constexpr int kBoxH = 18, kBoxW = 10, kBoxVox = kBoxH * kBoxW;  // halo'd input plane of a 16 x 8 tile
 constexpr int kSlotBytes = 12288;      // one box (11520 B) rounded up to the swizzle-atom alignment; the second M tile reads on
                                        // into whatever follows (rows >= 180 are never used)
-constexpr int kSlots = 3;
-constexpr int kTStride = 184;          // floats per tap row of a T plane (180 voxels padded)
-constexpr int kTPlane = 27 * kTStride; // floats per T plane
+constexpr int kSlots = 5;
+constexpr int kTStride = 184;          // floats per (kh,kw) row of an S plane (180 voxels padded)
+constexpr int kSPlane = 9 * kTStride;  // floats per S plane: the depth-summed taps of one OUTPUT plane, still un-shifted in (h, w)
+constexpr int kSRing = 4;              // S planes in shared memory
 constexpr int kTmemRing = 4;           // input planes whose T sits in TMEM (64 columns each)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +79,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+                 "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
 // descriptor version 1 at bit 46 (bit 14 of the high word), layout type at bits 61-63 (0 = none, 4 = 64-byte swizzle)
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo, uint32_t layout) { return ((sbo >> 4) & 0x3FFF) | (1u << 14) | (layout << 29); }
@@ -100,15 +110,15 @@ __global__ void __launch_bounds__(kClsThreads, 2) conv3d_cls_tc_kernel(const Cls
   const int lane = threadIdx.x & 31;
   uint8_t* slots_s = smem;
   uint8_t* b_s = slots_s + kSlots * kSlotBytes;       // weights [K chunk 4][n 32][8 x 16 bit] = 2 KB
-  float* t_s = reinterpret_cast<float*>(b_s + 2048);  // [3 planes][27 taps][kTStride]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(t_s + 3 * kTPlane);
+  float* s_s = reinterpret_cast<float*>(b_s + 2048);  // [kSRing planes][9 (kh,kw)][kTStride]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_s + kSRing * kSPlane);
   uint64_t* full_bar = bars;                     // [kSlots]    TMA -> MMA
   uint64_t* empty_bar = bars + kSlots;           // [kSlots]    MMA (commit) -> TMA
   uint64_t* tfull_bar = bars + 2 * kSlots;       // [kTmemRing] MMA (commit) -> extract warps
   uint64_t* tempty_bar = tfull_bar + kTmemRing;  // [kTmemRing] extract warps -> MMA
-  uint64_t* tready_bar = tempty_bar + kTmemRing; // [3] extract warps -> sum warps: T plane in shared memory
-  uint64_t* tfree_bar = tready_bar + 3;          // [3] sum warps -> extract warps: ring slot may be overwritten
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tfree_bar + 3);
+  uint64_t* sready_bar = tempty_bar + kTmemRing; // [kSRing] extract warps -> sum warps: S plane in shared memory
+  uint64_t* sfree_bar = sready_bar + kSRing;     // [kSRing] sum warps -> extract warps: ring slot may be overwritten
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sfree_bar + kSRing);
 
   // weights: B[n = tap][k = channel], K-major un-swizzled core matrices [k chunk][n][8]
   for (int e = threadIdx.x; e < 4 * 32 * 8; e += kClsThreads) {
@@ -125,9 +135,9 @@ __global__ void __launch_bounds__(kClsThreads, 2) conv3d_cls_tc_kernel(const Cls
       mbar_init(smem_u32(tfull_bar + i), 1);
       mbar_init(smem_u32(tempty_bar + i), kXW);
     }
-    for (int i = 0; i < 3; ++i) {
-      mbar_init(smem_u32(tready_bar + i), kXW);
-      mbar_init(smem_u32(tfree_bar + i), kSW);
+    for (int i = 0; i < kSRing; ++i) {
+      mbar_init(smem_u32(sready_bar + i), kXW);
+      mbar_init(smem_u32(sfree_bar + i), kSW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -201,76 +211,108 @@ __global__ void __launch_bounds__(kClsThreads, 2) conv3d_cls_tc_kernel(const Cls
       }
     }
   } else if (warp < kXW) {
-    // =========================================================== extract: T of every input plane, TMEM -> t_s[n % 3][tap][voxel]
-    uint32_t n = 0;
+    // =========================================================== extract: T of every input plane out of TMEM; depth sum in registers
+    // P1 = the kd = 0 taps of the previous plane (partial S of the current plane), P0 = kd 0 of two planes ago + kd 1 of the previous
+    // one (partial S of the previous plane); the current plane's kd = 2 taps complete S(ip - 1).  Tap index = kd * 9 + kh * 3 + kw.
+    // Warps 0 and 1 also own rows 128..191 of the second M tile (voxels 128..179 are real): Q0 / Q1.
+    uint32_t n = 0, m = 0;  // input planes consumed / output planes produced by this CTA so far
+    const int vox = warp * 32 + lane;
+    const bool second = warp < 2;
+    const bool vox2_ok = second && 128 + vox < kBoxVox;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int b, th, tw, o0, o1;
       decode(item, b, th, tw, o0, o1);
+      float P0[9], P1[9], Q0[9], Q1[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) P0[j] = P1[j] = Q0[j] = Q1[j] = 0.f;
       for (int pl = max(o0 - 1, 0); pl <= min(o1, p.D - 1); ++pl, ++n) {
         const uint32_t ts = n % kTmemRing, tphase = (n / kTmemRing) & 1;
-        const uint32_t rs = n % 3, rphase = (n / 3) & 1;
-        float* tp = t_s + (size_t)rs * kTPlane;
+        const bool emit = pl - 1 >= o0;  // S(pl - 1) is an output plane of this item (pl - 1 < o1 always holds)
+        float* sp = s_s + (size_t)(m % kSRing) * kSPlane;
+        if (emit) mbar_wait(smem_u32(sfree_bar + m % kSRing), ((m / kSRing) & 1) ^ 1);  // the sum warps are done with the plane that lived here
         mbar_wait(smem_u32(tfull_bar + ts), tphase);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ts * 64;
-        tmem_ld32(taddr, v0);
-        if (warp < 2) tmem_ld32(taddr + 32, v1);  // rows 128..191 of the second M tile (voxels 128..179 are real)
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // two 16-column loads per M tile (taps 16..31, then 0..15) keep 16 instead of 32 TMEM registers live next to the 36 partial sums
+        auto step = [&](uint32_t ta, float* A0, float* A1, int vx, bool st) {
+          uint32_t v[16];
+          tmem_ld16(ta + 16, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (st) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) sp[j * kTStride + vx] = A0[j] + __uint_as_float(v[2 + j]);  // taps 18..26 = kd 2
+          }
+          const float t16 = __uint_as_float(v[0]), t17 = __uint_as_float(v[1]);
+          tmem_ld16(ta, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 7; ++j) A0[j] = A1[j] + __uint_as_float(v[9 + j]);  // taps 9..15 = kd 1
+          A0[7] = A1[7] + t16, A0[8] = A1[8] + t17;
+#pragma unroll
+          for (int j = 0; j < 9; ++j) A1[j] = __uint_as_float(v[j]);              // taps 0..8 = kd 0
+        };
+        step(taddr, P0, P1, vox, emit);
+        if (second) step(taddr + 32, Q0, Q1, 128 + vox, emit && vox2_ok);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + ts));
-        mbar_wait(smem_u32(tfree_bar + rs), rphase ^ 1);  // the sum warps are done with the plane that lived in this slot
-        const int vox = warp * 32 + lane;
-#pragma unroll
-        for (int t = 0; t < 27; ++t) tp[t * kTStride + vox] = __uint_as_float(v0[t]);
-        if (warp < 2 && 128 + vox < kBoxVox) {
-#pragma unroll
-          for (int t = 0; t < 27; ++t) tp[t * kTStride + 128 + vox] = __uint_as_float(v1[t]);
+        if (lane == 0) {
+          mbar_arrive(smem_u32(tempty_bar + ts));
+          if (emit) mbar_arrive(smem_u32(sready_bar + m % kSRing));  // (mbarrier arrive has release semantics for the stores above)
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(tready_bar + rs));  // (mbarrier arrive has release semantics for the stores above)
+        if (emit) ++m;
+        if (pl == p.D - 1) {
+          // last plane of the volume: S(D - 1) has no kd = 2 term (zero padding along depth) -- it is complete now
+          float* sq = s_s + (size_t)(m % kSRing) * kSPlane;
+          mbar_wait(smem_u32(sfree_bar + m % kSRing), ((m / kSRing) & 1) ^ 1);
+#pragma unroll
+          for (int j = 0; j < 9; ++j) {
+            sq[j * kTStride + vox] = P0[j];
+            if (vox2_ok) sq[j * kTStride + 128 + vox] = Q0[j];
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(sready_bar + m % kSRing));
+          ++m;
+        }
       }
     }
   } else {
-    // =========================================================== sum: out[od] = sum over kd of the 9 shifted taps of T(od-1+kd)
-    // output voxel of the tile: sum warp s takes tile rows s, s+4, s+8, s+12 (8 columns each).  A T plane keeps the 18 x 10 halo'd
+    // =========================================================== sum: out[od][h][w] = sum over (kh, kw) of S(od)[(h-1+kh, w-1+kw)][kh,kw]
+    // output voxel of the tile: sum warp s takes tile rows s, s+4, s+8, s+12 (8 columns each).  An S plane keeps the 18 x 10 halo'd
     // box with a row pitch of 10 floats: rows 4 apart start 40 floats = 8 banks apart, so the warp's four 8-wide windows fall on 32
-    // distinct banks for every tap -- with four CONSECUTIVE rows (pitch 10) rows 0 and 3 overlapped on 6 banks and every one of the 27
-    // LDS was a 2-way conflict (ncu r02: 44 % of the shared-memory wavefronts of this kernel, LSU pipe 76 %)
+    // distinct banks for every tap (four CONSECUTIVE rows overlap on 6 banks: every LDS a 2-way conflict).
     const int hl = (warp - kXW) + 4 * (lane >> 3), wl = lane & 7;
-    uint32_t nbase = 0;  // sequence number of the item's first input plane
+    uint32_t m = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int b, th, tw, o0, o1;
       decode(item, b, th, tw, o0, o1);
       const int oh = th * 16 + hl, ow = tw * 8 + wl;
       const bool ok = oh < p.H && ow < p.W;
-      const int pl0 = max(o0 - 1, 0), pl1 = min(o1, p.D - 1);
-      for (int od = o0; od < o1; ++od) {
-        const size_t o = (((size_t)b * p.D + od) * p.H + oh) * p.W + ow;
-        const float r = (ok && p.res) ? __ldg(p.res + o) : 0.f;
-        float acc[3] = {0.f, 0.f, 0.f};
+      // The fp32 residual of a plane is fetched TWO planes ahead: a plane's sum is a few hundred cycles of work, a DRAM round trip
+      // several times that.
+      const size_t plane = (size_t)p.H * p.W;
+      const size_t o_first = (((size_t)b * p.D + o0) * p.H + oh) * p.W + ow;
+      const bool has_r = ok && p.res != nullptr;
+      float r0 = has_r ? __ldg(p.res + o_first) : 0.f;
+      float r1 = (has_r && o0 + 1 < o1) ? __ldg(p.res + o_first + plane) : 0.f;
+      for (int od = o0; od < o1; ++od, ++m) {
+        const size_t o = o_first + (size_t)(od - o0) * plane;
+        const float r = r0;
+        r0 = r1;
+        r1 = (has_r && od + 2 < o1) ? __ldg(p.res + o + 2 * plane) : 0.f;
+        const uint32_t rs = m % kSRing;
+        mbar_wait(smem_u32(sready_bar + rs), (m / kSRing) & 1);
+        const float* sq = s_s + (size_t)rs * kSPlane + hl * kBoxW + wl;
+        float acc[3];
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd) {
-          const int ip = od - 1 + kd;
-          if (ip < 0 || ip >= p.D) continue;  // zero padding along depth
-          const uint32_t n = nbase + (uint32_t)(ip - pl0);
-          const uint32_t rs = n % 3, rphase = (n / 3) & 1;
-          mbar_wait(smem_u32(tready_bar + rs), rphase);
-          const float* tq = t_s + (size_t)rs * kTPlane + kd * 9 * kTStride + hl * kBoxW + wl;
+        for (int kh = 0; kh < 3; ++kh) {
+          acc[kh] = sq[(kh * 3) * kTStride + kh * kBoxW];
 #pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) acc[kd] += tq[(kh * 3 + kw) * kTStride + kh * kBoxW + kw];
-          // T(ip) is last used as the kd = 0 plane of output ip + 1, or -- at the end of a chunk -- by the chunk's last output
-          if (kd == 0 || od == o1 - 1) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(tfree_bar + rs));
-          }
+          for (int kw = 1; kw < 3; ++kw) acc[kh] += sq[(kh * 3 + kw) * kTStride + kh * kBoxW + kw];
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(sfree_bar + rs));
         if (ok) p.out[o] = (acc[0] + acc[1]) + acc[2] + r;
       }
-      nbase += (uint32_t)(pl1 - pl0 + 1);
     }
   }
   tc_fence_before();
@@ -324,7 +366,7 @@ extern "C" int mode_conv3d_classifier_tc(const mode_h16* x, const float* w, cons
   }
   p.chunk = best_chunk, p.nchunks = ceil_div(D, best_chunk);
   p.nitems = cols * p.nchunks;
-  const size_t smem = 1024 + (size_t)kSlots * kSlotBytes + 2048 + (size_t)3 * kTPlane * 4 + (2 * kSlots + 2 * kTmemRing + 6) * 8 + 16;
+  const size_t smem = 1024 + (size_t)kSlots * kSlotBytes + 2048 + (size_t)kSRing * kSPlane * 4 + (2 * kSlots + 2 * kTmemRing + 2 * kSRing) * 8 + 16;
   static thread_local bool attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
   bool& attr = attr_dev[current_device()];
   if (!attr) {

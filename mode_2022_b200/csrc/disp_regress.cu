@@ -97,6 +97,103 @@ __global__ void __launch_bounds__(kRegThreads) disp_regress_kernel(const float* 
   }
 }
 
+// ---- maxdisp 192 at image widths that are multiples of 256 (every BASELINE config): the kernel above is instruction-issue bound
+// (ncu r02: 2700 warp instructions per 32 pixels against 1536 MUFU cycles, issue slots 54 % used, long-scoreboard stalls on the
+// 192 L1/L2 logit loads per thread).  Here
+//   * a block = 256 consecutive pixels of ONE image row, so the row interpolation weights (lh0, lh1) are block constants: the block
+//     first builds the row-interpolated coarse logits u[d4][col] = lh0 * c[d4][h0][col] + lh1 * c[d4][h1][col] for its <= 66 coarse
+//     columns in shared memory (coalesced loads, all in flight at once), and a pixel's 48 bilinear logits are
+//     t[d4] = lw0 * u[d4][w0] + lw1 * u[d4][w1] -- ATen's trilinear formula with the h- and w-lerp exchanged (same value up to one
+//     fp32 rounding of a logit, far inside the 1e-4 disparity budget; measured in tests/test_gpu_kernels.py);
+//   * those 48 logits stay in REGISTERS (every index of the unrolled fine-depth loop is a compile-time constant), pre-shifted by the
+//     maximum and pre-scaled by log2(e): a fine plane is FFMA (depth lerp t0 + l1 (t1 - t0), the difference shared by the ~4 planes
+//     of a coarse interval), MUFU.EX2, FADD, FFMA -- 4.25 instructions against 8 MUFU cycles per warp;
+//   * the three confidence planes (run-time indices) re-evaluate their logits from the shared-memory tile with the same
+//     expressions, so P[r], P[r-1], P[r+1] are the very numbers the softmax sum was built from.
+constexpr int kTileCols = 66;  // 255 * (W4-1)/(W-1) < 63.75 -> at most 64 + 2 coarse columns per block
+
+__global__ void __launch_bounds__(kRegThreads, 3) disp_regress_192_kernel(const float* __restrict__ cost, float* __restrict__ pred, float* __restrict__ conf, int H4,
+                                                                          int W4, int H, int W, float sh, float sw) {
+  constexpr int D4 = 48, D = 192;
+  constexpr float sd = (float)(D4 - 1) / (float)(D - 1);
+  constexpr float kLog2e = 1.4426950408889634f;
+  __shared__ float tile[D4][kTileCols];
+  const int wblks = W / kRegThreads;
+  const int h = blockIdx.x / wblks, wb = (blockIdx.x - h * wblks) * kRegThreads;
+  const int b = blockIdx.y;
+  const float hs = sh * h;
+  const int h0 = (int)hs;
+  const int h1 = h0 + (h0 < H4 - 1);
+  const float lh1 = hs - h0, lh0 = 1.f - lh1;
+  const int c_lo = (int)(sw * wb);  // w0 of the block's first pixel (w0 is monotone in w)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* r0 = cost + ((size_t)b * D4 * H4 + h0) * W4;
+    const float* r1 = cost + ((size_t)b * D4 * H4 + h1) * W4;
+    const int g0 = min(c_lo + lane, W4 - 1), g1 = min(c_lo + lane + 32, W4 - 1), g2 = min(c_lo + lane + 64, W4 - 1);
+#pragma unroll
+    for (int j = 0; j < D4 / 8; ++j) {
+      const int d4 = warp + 8 * j;
+      const size_t po = (size_t)d4 * H4 * W4;
+      tile[d4][lane] = lh0 * __ldg(r0 + po + g0) + lh1 * __ldg(r1 + po + g0);
+      tile[d4][lane + 32] = lh0 * __ldg(r0 + po + g1) + lh1 * __ldg(r1 + po + g1);
+      if (lane < kTileCols - 64) tile[d4][lane + 64] = lh0 * __ldg(r0 + po + g2) + lh1 * __ldg(r1 + po + g2);
+    }
+  }
+  __syncthreads();
+  const int w = wb + threadIdx.x;
+  const float ws = sw * w;
+  const int w0 = (int)ws;
+  const int w1 = w0 + (w0 < W4 - 1);
+  const float lw1 = ws - w0, lw0 = 1.f - lw1;
+  const int i0 = w0 - c_lo, i1 = w1 - c_lo;
+  auto coarse = [&](int d4) { return lw0 * tile[d4][i0] + lw1 * tile[d4][i1]; };
+  float t[D4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int d4 = 0; d4 < D4; ++d4) {
+    t[d4] = coarse(d4);
+    m = fmaxf(m, t[d4]);
+  }
+  const float mneg = -m * kLog2e;
+#pragma unroll
+  for (int d4 = 0; d4 < D4; ++d4) t[d4] = fmaf(t[d4], kLog2e, mneg);  // (t - m) log2(e)
+  float sum = 0.f, wsum = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float ds = sd * d;
+    const int d0 = (int)ds;
+    const int d1 = d0 + (d0 < D4 - 1);
+    const float l1 = ds - d0;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l1, t[d1] - t[d0], t[d0])));
+    sum += e;
+    wsum = fmaf(e, (float)d, wsum);
+  }
+  const float pr = wsum / sum;
+  const size_t o = ((size_t)b * H + h) * W + w;
+  pred[o] = pr;
+  if (conf != nullptr) {
+    const int r = (int)rintf(pr);  // torch.round: half-to-even (mode_disparity.py:159)
+    const float inv = 1.f / sum;
+    float c = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {  // order of the reference's three grid_samples: r, r-1, r+1
+      int d = r + (k == 0 ? 0 : (k == 1 ? -1 : 1));
+      d = min(max(d, 0), D - 1);
+      const float ds = sd * d;
+      const int d0 = (int)ds;
+      const int d1 = d0 + (d0 < D4 - 1);
+      const float l1 = ds - d0;
+      const float t0 = fmaf(coarse(d0), kLog2e, mneg), t1 = fmaf(coarse(d1), kLog2e, mneg);
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l1, t1 - t0, t0)));
+      c += e * inv;
+    }
+    conf[o] = c;
+  }
+}
+
 extern "C" int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4, int H4, int W4, int D, int H, int W,
                                  void* stream) {
   MODE_CHECK_ARG(cost && pred, "disp_regress: null pointer");
@@ -110,6 +207,12 @@ extern "C" int mode_disp_regress(const float* cost, float* pred, float* conf, in
     MODE_CHECK_CUDA(cudaFuncSetAttribute(disp_regress_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "disp_regress");
     MODE_CHECK_CUDA(cudaFuncSetAttribute(disp_regress_kernel<48, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "disp_regress");
     attr_set_for = (int)smem;
+  }
+  if (D4 == 48 && D == 192 && W % kRegThreads == 0 && W4 * 4 == W && W4 >= 2) {
+    dim3 grid192((unsigned)((long long)H * (W / kRegThreads)), B);
+    disp_regress_192_kernel<<<grid192, kRegThreads, 0, (cudaStream_t)stream>>>(cost, pred, conf, H4, W4, H, W, sh, sw);
+    MODE_CHECK_LAUNCH("disp_regress");
+    return MODE_OK;
   }
   dim3 grid(ceil_div((long long)H * W, kRegThreads), B);
   if (D4 == 48 && D == 192)

@@ -66,6 +66,26 @@ def test_disp_regress(ops, d4, h4, w4):
   assert conf.max().item() <= 2.0 + 1e-5  # border clamp can count a bin twice
 
 
+@pytest.mark.parametrize('h4,w4,scale', [(8, 64, 4.0), (5, 128, 1.0), (16, 256, 12.0)])
+def test_disp_regress_maxdisp192_row_tile_kernel(ops, h4, w4, scale):
+  """maxdisp 192 with W % 256 == 0 (every BASELINE shape) runs the row-tile kernel: row-interpolated coarse tile in shared memory,
+  logits in registers, confidence planes re-evaluated from the tile.  Same bounds as the generic kernel; `scale` 12 saturates most
+  posteriors."""
+  g = torch.Generator().manual_seed(h4 + w4)
+  cost = torch.randn(2, 1, 48, h4, w4, generator=g) * scale
+  D, H, W = 192, 4 * h4, 4 * w4
+  pred_o, conf_o = O.disparity_regression(cost, D, H, W, want_conf=True)
+  pred, conf = ops.disp_regress(cost.cuda(), D, H, W)
+  pred, conf = pred.cpu(), conf.cpu()
+  assert torch.isfinite(pred).all() and torch.isfinite(conf).all()
+  assert ((pred - pred_o).abs() / pred_o.abs().clamp_min(1.0)).max().item() <= 1e-4
+  same_r = torch.round(pred) == torch.round(pred_o)
+  assert same_r.float().mean().item() > 0.999
+  assert ((conf - conf_o).abs() * same_r).max().item() <= 2e-5
+  assert conf.max().item() <= 2.0 + 1e-5
+  assert torch.equal(ops.disp_regress(cost.cuda(), D, H, W)[0].cpu(), pred)  # deterministic
+
+
 def test_disp_regress_one_hot_extremes(ops):
   """Saturated logits pin the disparity to {0, D-1} and the confidence to 2.0 at the border (clamp double count)."""
   cost = torch.full((1, 1, 4, 4, 4), -50.0)
