@@ -24,7 +24,7 @@ using namespace mode;
 
 namespace {
 
-constexpr int kXW = 4, kSW = 4;                    // extract warps (TMEM lane quadrant = warp id), sum warps
+constexpr int kXW = 6, kSW = 4;                    // extract warps (0-3: M tile 0, 4-5: rows 128..191 of M tile 1; TMEM lane quadrant = warp % 4), sum warps
 constexpr int kClsThreads = (kXW + kSW + 2) * 32;  // + MMA warp, TMA producer
 constexpr int kBoxH = 18, kBoxW = 10, kBoxVox = kBoxH * kBoxW;  // halo'd input plane of a 16 x 8 tile
 constexpr int kSlotBytes = 12288;      // one box (11520 B) rounded up to the swizzle-atom alignment; the second M tile reads on
@@ -78,13 +78,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[31])
       : "r"(taddr)
       : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
-                 "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr)
-               : "memory");
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFF) | (((lbo >> 4) & 0x3FFF) << 16); }
 // descriptor version 1 at bit 46 (bit 14 of the high word), layout type at bits 61-63 (0 = none, 4 = 64-byte swizzle)
@@ -214,60 +207,49 @@ __global__ void __launch_bounds__(kClsThreads, 2) conv3d_cls_tc_kernel(const Cls
     // =========================================================== extract: T of every input plane out of TMEM; depth sum in registers
     // P1 = the kd = 0 taps of the previous plane (partial S of the current plane), P0 = kd 0 of two planes ago + kd 1 of the previous
     // one (partial S of the previous plane); the current plane's kd = 2 taps complete S(ip - 1).  Tap index = kd * 9 + kh * 3 + kw.
-    // Warps 0 and 1 also own rows 128..191 of the second M tile (voxels 128..179 are real): Q0 / Q1.
+    // Warps 0-3 own the 128 rows of the first M tile, warps 4-5 rows 128..191 of the second (voxels 128..179 are real): one TMEM load
+    // per warp and plane.
     uint32_t n = 0, m = 0;  // input planes consumed / output planes produced by this CTA so far
-    const int vox = warp * 32 + lane;
-    const bool second = warp < 2;
-    const bool vox2_ok = second && 128 + vox < kBoxVox;
+    const int vox = warp * 32 + lane;  // warps 4, 5: 128 + (warp - 4) * 32 + lane
+    const bool vox_ok = vox < kBoxVox;
+    const uint32_t tsub = ((uint32_t)((warp & 3) * 32) << 16) + (warp >= 4 ? 32u : 0u);  // lane quadrant, column block of the M tile
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       int b, th, tw, o0, o1;
       decode(item, b, th, tw, o0, o1);
-      float P0[9], P1[9], Q0[9], Q1[9];
+      float P0[9], P1[9];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) P0[j] = P1[j] = Q0[j] = Q1[j] = 0.f;
+      for (int j = 0; j < 9; ++j) P0[j] = P1[j] = 0.f;
       for (int pl = max(o0 - 1, 0); pl <= min(o1, p.D - 1); ++pl, ++n) {
         const uint32_t ts = n % kTmemRing, tphase = (n / kTmemRing) & 1;
         const bool emit = pl - 1 >= o0;  // S(pl - 1) is an output plane of this item (pl - 1 < o1 always holds)
         float* sp = s_s + (size_t)(m % kSRing) * kSPlane;
-        if (emit) mbar_wait(smem_u32(sfree_bar + m % kSRing), ((m / kSRing) & 1) ^ 1);  // the sum warps are done with the plane that lived here
         mbar_wait(smem_u32(tfull_bar + ts), tphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ts * 64;
-        // two 16-column loads per M tile (taps 16..31, then 0..15) keep 16 instead of 32 TMEM registers live next to the 36 partial sums
-        auto step = [&](uint32_t ta, float* A0, float* A1, int vx, bool st) {
-          uint32_t v[16];
-          tmem_ld16(ta + 16, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (st) {
-#pragma unroll
-            for (int j = 0; j < 9; ++j) sp[j * kTStride + vx] = A0[j] + __uint_as_float(v[2 + j]);  // taps 18..26 = kd 2
-          }
-          const float t16 = __uint_as_float(v[0]), t17 = __uint_as_float(v[1]);
-          tmem_ld16(ta, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 7; ++j) A0[j] = A1[j] + __uint_as_float(v[9 + j]);  // taps 9..15 = kd 1
-          A0[7] = A1[7] + t16, A0[8] = A1[8] + t17;
-#pragma unroll
-          for (int j = 0; j < 9; ++j) A1[j] = __uint_as_float(v[j]);              // taps 0..8 = kd 0
-        };
-        step(taddr, P0, P1, vox, emit);
-        if (second) step(taddr + 32, Q0, Q1, 128 + vox, emit && vox2_ok);
+        uint32_t v[32];
+        tmem_ld32(tmem_base + tsub + ts * 64, v);
+        if (emit) mbar_wait(smem_u32(sfree_bar + m % kSRing), ((m / kSRing) & 1) ^ 1);  // the sum warps are done with the plane that lived here
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(tempty_bar + ts));
-          if (emit) mbar_arrive(smem_u32(sready_bar + m % kSRing));  // (mbarrier arrive has release semantics for the stores above)
+        if (lane == 0) mbar_arrive(smem_u32(tempty_bar + ts));
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          if (emit && vox_ok) sp[j * kTStride + vox] = P0[j] + __uint_as_float(v[18 + j]);
+          P0[j] = P1[j] + __uint_as_float(v[9 + j]);
+          P1[j] = __uint_as_float(v[j]);
         }
-        if (emit) ++m;
+        if (emit) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(sready_bar + m % kSRing));  // (mbarrier arrive has release semantics for the stores above)
+          ++m;
+        }
         if (pl == p.D - 1) {
           // last plane of the volume: S(D - 1) has no kd = 2 term (zero padding along depth) -- it is complete now
           float* sq = s_s + (size_t)(m % kSRing) * kSPlane;
           mbar_wait(smem_u32(sfree_bar + m % kSRing), ((m / kSRing) & 1) ^ 1);
+          if (vox_ok) {
 #pragma unroll
-          for (int j = 0; j < 9; ++j) {
-            sq[j * kTStride + vox] = P0[j];
-            if (vox2_ok) sq[j * kTStride + 128 + vox] = Q0[j];
+            for (int j = 0; j < 9; ++j) sq[j * kTStride + vox] = P0[j];
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(sready_bar + m % kSRing));
