@@ -107,7 +107,8 @@ def _sphere_case(B, C, Co, h, w, st, seed):
   return x, wgt, pos
 
 
-@pytest.mark.parametrize('B,C,Co,h,w,st', [(1, 1, 1, 5, 10, 'ERP'), (2, 8, 16, 16, 8, 'Cassini'), (1, 64, 128, 32, 16, 'Cassini'), (1, 128, 128, 16, 32, 'ERP'), (1, 5, 33, 16, 8, 'Cassini')])
+@pytest.mark.parametrize('B,C,Co,h,w,st', [(1, 1, 1, 5, 10, 'ERP'), (2, 8, 16, 16, 8, 'Cassini'), (1, 64, 128, 32, 16, 'Cassini'), (1, 128, 128, 16, 32, 'ERP'), (1, 5, 33, 16, 8, 'Cassini'),
+                                                 (2, 16, 40, 10, 20, 'ERP'), (1, 8, 136, 6, 3, 'Cassini'), (1, 24, 200, 20, 10, 'Cassini')])
 def test_sphere_conv_f32_vs_oracle(ops, B, C, Co, h, w, st):
   x, wgt, pos = _sphere_case(B, C, Co, h, w, st, 3)
   want = O.sphere_conv(x, pos, wgt)
