@@ -55,6 +55,9 @@ __device__ __forceinline__ void fix_add(long long* p, float v, float scale) {
 }
 template <bool DET>
 __device__ __forceinline__ void acc_add(float* fp, long long* ip, size_t idx, float v, float scale) {
+#ifdef SPHERE_EXP_NOSCATTER  // timing experiment (wrong results): the accumulation is skipped unless a value is NaN
+  if (v == v) return;
+#endif
   if (DET)
     fix_add(ip + idx, v, scale);
   else

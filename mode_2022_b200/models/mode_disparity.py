@@ -26,6 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
+from .batchnorm import BatchNorm3d
 from .submodule import bn_affine, convbn, convbn_3d, sphere_feature_extraction
 
 
@@ -39,8 +40,8 @@ class hourglass(nn.Module):
     self.conv3 = nn.Sequential(convbn_3d(inplanes * 2, inplanes * 2, kernel_size=3, stride=2, pad=1), nn.ReLU(inplace=True))
     self.conv4 = nn.Sequential(convbn_3d(inplanes * 2, inplanes * 2, kernel_size=3, stride=1, pad=1), nn.ReLU(inplace=True))
     self.conv5 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes * 2, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False),
-                               nn.BatchNorm3d(inplanes * 2))
-    self.conv6 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False), nn.BatchNorm3d(inplanes))
+                               BatchNorm3d(inplanes * 2))
+    self.conv6 = nn.Sequential(nn.ConvTranspose3d(inplanes * 2, inplanes, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False), BatchNorm3d(inplanes))
 
   def forward(self, x, presqu, postsqu):
     """Training path (reference mode_disparity.py:27-46)."""

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .batchnorm import BatchNorm2d
 from .submodule import convbn
 
 
@@ -44,7 +45,7 @@ class feature_extraction(nn.Module):
   def _make_layer(self, planes, blocks, stride, pad, dilation):
     downsample = None
     if stride != 1 or self.inplanes != planes:
-      downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes, kernel_size=1, stride=stride, bias=False), nn.BatchNorm2d(planes))
+      downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes, kernel_size=1, stride=stride, bias=False), BatchNorm2d(planes))
     layers = [BasicBlock(self.inplanes, planes, stride, downsample, pad, dilation)]
     self.inplanes = planes
     layers += [BasicBlock(planes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]

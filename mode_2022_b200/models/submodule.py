@@ -9,24 +9,25 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .batchnorm import BatchNorm2d, BatchNorm3d
 from .sphere_conv import SphereConv
 
 
 def convbn(in_planes, out_planes, kernel_size, stride, pad, dilation):
   """Conv2d + BN (reference submodule.py:15-17)."""
   return nn.Sequential(nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=dilation if dilation > 1 else pad, dilation=dilation, bias=False),
-                       nn.BatchNorm2d(out_planes))
+                       BatchNorm2d(out_planes))
 
 
 def convbn_3d(in_planes, out_planes, kernel_size, stride, pad):
   """Conv3d + BN (reference submodule.py:20-22)."""
-  return nn.Sequential(nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, padding=pad, stride=stride, bias=False), nn.BatchNorm3d(out_planes))
+  return nn.Sequential(nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, padding=pad, stride=stride, bias=False), BatchNorm3d(out_planes))
 
 
 def sphereConvbn(in_height, in_width, sphereType, in_planes, out_planes, kernel_size, stride, pad, dilation):
   """SphereConv + BN (reference submodule.py:61-75)."""
   return nn.Sequential(SphereConv(in_height, in_width, sphereType, in_planes, out_planes, kernel_size=kernel_size, stride=stride,
-                                  padding=dilation if dilation > 1 else pad, dilation=dilation, bias=False), nn.BatchNorm2d(out_planes))
+                                  padding=dilation if dilation > 1 else pad, dilation=dilation, bias=False), BatchNorm2d(out_planes))
 
 
 class RegularBasicBlock(nn.Module):
@@ -103,7 +104,7 @@ class sphere_feature_extraction(nn.Module):
   def _make_layer(block, height, width, sphereType, inplanes, planes, blocks, stride, pad, dilation):
     downsample = None
     if stride != 1 or inplanes != planes * block.expansion:
-      downsample = nn.Sequential(nn.Conv2d(inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False), nn.BatchNorm2d(planes * block.expansion))
+      downsample = nn.Sequential(nn.Conv2d(inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False), BatchNorm2d(planes * block.expansion))
     if block is SphereBasicBlock:
       layers = [block(height, width, sphereType, inplanes, planes, stride, downsample, pad, dilation)]
       layers += [block(height // stride, width // stride, sphereType, planes, planes, 1, None, pad, dilation) for _ in range(1, blocks)]

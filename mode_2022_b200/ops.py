@@ -262,6 +262,79 @@ torch.library.register_autograd('mode_b200::disp_regress', _disp_regress_bwd, se
 
 
 # ------------------------------------------------------------------------------------------------
+# f1. training-mode BatchNorm (batch statistics)
+# ------------------------------------------------------------------------------------------------
+def _bn_dims(x: torch.Tensor):
+  if x.dim() < 3:
+    raise ValueError('batch_norm_train: expected (N, C, spatial...) input')
+  n, c = x.shape[0], x.shape[1]
+  return n, c, x.numel() // (n * c)
+
+
+def _bn_workspace(x: torch.Tensor, n: int, c: int, s: int) -> torch.Tensor:
+  return torch.empty((_lib.load().mode_batchnorm_workspace_bytes(c, n, s) + 15) // 16 * 2, dtype=torch.float64, device=x.device)
+
+
+@torch.library.custom_op('mode_b200::batch_norm_train', mutates_args=())
+@_device_guard
+def batch_norm_train(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+  """Training-mode BatchNorm of a (N, C, *spatial) fp32 tensor (nn.BatchNorm2d / 3d as the reference trains them, models/submodule.py:14-30):
+  returns (y, batch mean, 1/sqrt(biased var + eps), unbiased batch variance).  Functional: the module (models/batchnorm.py) applies the
+  momentum update of the running statistics from the returned vectors."""
+  x = _chk(x, torch.float32, 'batch_norm_train')
+  n, c, s = _bn_dims(x)
+  weight, bias = _opt(weight, torch.float32, 'batch_norm_train'), _opt(bias, torch.float32, 'batch_norm_train')
+  y = torch.empty_like(x)
+  mean, invstd, var_u = x.new_empty(c), x.new_empty(c), x.new_empty(c)
+  ws = _bn_workspace(x, n, c, s)
+  _lib.call('mode_batchnorm_train_fwd_f32', _p(x), _p(weight), _p(bias), _p(y), _p(mean), _p(invstd), _p(var_u), None, None, _p(ws), n, c, s, float(eps), 0.0, _stream())
+  return y, mean, invstd, var_u
+
+
+@batch_norm_train.register_fake
+def _(x, weight, bias, eps):
+  c = x.shape[1]
+  return torch.empty_like(x), x.new_empty(c), x.new_empty(c), x.new_empty(c)
+
+
+@torch.library.custom_op('mode_b200::batch_norm_train_backward', mutates_args=())
+@_device_guard
+def batch_norm_train_backward(x: torch.Tensor, grad_y: torch.Tensor, weight: Optional[torch.Tensor], save_mean: torch.Tensor,
+                              save_invstd: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+  """(grad_x, grad_weight, grad_bias) of batch_norm_train."""
+  x, grad_y = _chk(x, torch.float32, 'batch_norm_train_backward'), _chk(grad_y, torch.float32, 'batch_norm_train_backward')
+  n, c, s = _bn_dims(x)
+  gx = torch.empty_like(x)
+  gw, gb = x.new_empty(c), x.new_empty(c)
+  ws = _bn_workspace(x, n, c, s)
+  _lib.call('mode_batchnorm_train_bwd_f32', _p(x), _p(grad_y), _p(_opt(weight, torch.float32, 'batch_norm_train_backward')), _p(save_mean), _p(save_invstd), _p(gx), _p(gw),
+            _p(gb), _p(ws), n, c, s, _stream())
+  return gx, gw, gb
+
+
+@batch_norm_train_backward.register_fake
+def _(x, grad_y, weight, save_mean, save_invstd):
+  return torch.empty_like(x), x.new_empty(x.shape[1]), x.new_empty(x.shape[1])
+
+
+def _bn_setup(ctx, inputs, output):
+  x, weight, bias, eps = inputs
+  _, mean, invstd, _ = output
+  ctx.save_for_backward(x, weight, mean, invstd)
+  ctx.has_weight, ctx.has_bias = weight is not None, bias is not None
+
+
+def _bn_bwd(ctx, grad_y, grad_mean, grad_invstd, grad_var):
+  """Gradient through y only: the statistics outputs feed the (non-differentiable) running-stat update."""
+  x, weight, mean, invstd = ctx.saved_tensors
+  gx, gw, gb = batch_norm_train_backward(x, grad_y.contiguous(), weight, mean, invstd)
+  return gx, (gw if ctx.has_weight else None), (gb if ctx.has_bias else None), None
+
+
+torch.library.register_autograd('mode_b200::batch_norm_train', _bn_bwd, setup_context=_bn_setup)
+
+
+# ------------------------------------------------------------------------------------------------
 # a2. spherical convolution
 # ------------------------------------------------------------------------------------------------
 

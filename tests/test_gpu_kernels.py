@@ -595,3 +595,56 @@ def test_sphere_conv_backward_is_run_to_run_deterministic(ops):
     del os.environ['MODE_B200_NONDETERMINISTIC_BWD']
   for a, b in zip(runs[0], ref):
     assert (a - b).abs().max().item() <= 2e-5 * max(b.abs().max().item(), 1e-12)
+
+
+# ---------------------------------------------------------------------------- f1 training-mode BatchNorm
+@pytest.mark.parametrize('shape', [(2, 32, 12, 64, 32), (1, 64, 6, 32, 16), (3, 5, 7, 9), (2, 128, 64, 32), (4, 3, 5, 7, 3), (1, 8, 2, 2)])
+def test_batch_norm_train_vs_torch(ops, shape):
+  """mode_b200::batch_norm_train (+ backward) == F.batch_norm(training=True) of torch on the same GPU: output, saved statistics,
+  running-stat update (momentum 0.1, unbiased variance), grad_input / grad_weight / grad_bias.  Shapes cover NCHW and NCDHW, vector
+  (S % 4 == 0) and scalar paths, a non-zero mean much larger than the spread (shifted-sum statistics)."""
+  from mode_2022_b200.models.batchnorm import BatchNorm2d, BatchNorm3d
+  g = torch.Generator().manual_seed(sum(shape))
+  C = shape[1]
+  x = (torch.randn(*shape, generator=g) * 0.7 + 30.0 * torch.randn(1, C, *([1] * (len(shape) - 2)), generator=g)).cuda()
+  gy = torch.randn(*shape, generator=g).cuda()
+  cls_t, cls_m = (torch.nn.BatchNorm3d, BatchNorm3d) if len(shape) == 5 else (torch.nn.BatchNorm2d, BatchNorm2d)
+  ref, got = cls_t(C).cuda().train(), cls_m(C).cuda().train()
+  with torch.no_grad():
+    ref.weight.copy_(torch.rand(C, generator=g) + 0.5), ref.bias.copy_(torch.randn(C, generator=g))
+  got.load_state_dict(ref.state_dict())
+  assert list(got.state_dict().keys()) == list(ref.state_dict().keys())
+  xr, xg = x.clone().requires_grad_(), x.clone().requires_grad_()
+  for _ in range(2):  # two steps: the running statistics accumulate
+    yr, yg = ref(xr), got(xg)
+  yr.backward(gy), yg.backward(gy)
+  x64 = x.double()
+  dims = [0] + list(range(2, x.dim()))
+  truth = ((x64 - x64.mean(dims, keepdim=True)) / torch.sqrt(x64.var(dims, unbiased=False, keepdim=True) + 1e-5)) * ref.weight.double().view(1, C, *([1] * (x.dim() - 2))) \
+      + ref.bias.double().view(1, C, *([1] * (x.dim() - 2)))
+  err_ref, err_got = (yr.double() - truth).abs().max().item(), (yg.double() - truth).abs().max().item()
+  assert err_got <= max(2 * err_ref, 2e-5), (err_got, err_ref)  # at least as close to the fp64 truth as cuDNN
+  assert torch.allclose(got.running_mean, ref.running_mean, rtol=1e-5, atol=1e-5) and torch.allclose(got.running_var, ref.running_var, rtol=1e-4, atol=1e-6)
+  assert int(got.num_batches_tracked) == int(ref.num_batches_tracked) == 2
+  scale = max(1.0, xr.grad.abs().max().item())
+  assert (xg.grad - xr.grad).abs().max().item() <= 5e-4 * scale  # dx is a difference of O(1) terms scaled by 1/sigma: conditioning of the op
+  assert torch.allclose(got.weight.grad, ref.weight.grad, rtol=2e-4, atol=2e-3) and torch.allclose(got.bias.grad, ref.bias.grad, rtol=2e-4, atol=2e-3)
+  # eval mode, momentum=None (cumulative average: the BN calibration of the fixtures) fall back to torch's implementation
+  got.load_state_dict(ref.state_dict())
+  got.eval(), ref.eval()
+  assert torch.equal(got(x), ref(x))
+  got.train(), ref.train()
+  got.momentum = ref.momentum = None
+  assert torch.equal(got(x), ref(x)) and torch.equal(got.running_var, ref.running_var)
+
+
+def test_batch_norm_train_deterministic_and_opcheck(ops):
+  from torch.library import opcheck
+  x = torch.randn(2, 16, 4, 8, 8, device='cuda')
+  w, b = torch.rand(16, device='cuda') + 0.5, torch.randn(16, device='cuda')
+  a = ops.batch_norm_train(x, w, b, 1e-5)
+  for _ in range(3):
+    c = ops.batch_norm_train(x, w, b, 1e-5)
+    assert all(torch.equal(u, v) for u, v in zip(a, c))
+  opcheck(torch.ops.mode_b200.batch_norm_train.default, (x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_(), 1e-5),
+          test_utils=('test_schema', 'test_faketensor', 'test_autograd_registration'))
