@@ -178,15 +178,18 @@ int mode_depth_view_trans(const float* depth, const double* depth64, const float
  * models/mode_disparity.py:11-46,66-80; train_disparity.py:147-163): y = (x - mean_B) / sqrt(var_B + eps) * gamma + beta with the
  * biased batch variance; save_mean / save_invstd (C) are returned for the backward pass, batch_var (C, unbiased, may be NULL) for a
  * caller that updates the running statistics itself, and running_mean / running_var (may be NULL) are updated in place with
- * `momentum` (unbiased variance) when given.  x, y, dy, dx: (N, C, S) contiguous fp32 (S = H*W or D*H*W); gamma / beta / running_* may be NULL.
+ * `momentum` (unbiased variance) when given.  x, y, dy, dx: fp32, (N, C, S) contiguous (S = H*W or D*H*W), or with channels_last != 0
+ * (N, S, C) in memory (torch.channels_last / channels_last_3d: what cuDNN's tensor-core conv3d kernels consume without layout
+ * transforms; C a power of two in [4, 256]); gamma / beta may be NULL.
  * workspace: mode_batchnorm_workspace_bytes(C, N, S) bytes, 16-byte aligned, caller-allocated (fp64 partial sums, combined in a
  * fixed order: the statistics and parameter gradients are bit-reproducible).
  * backward: dx, dgamma (C), dbeta (C) are OVERWRITTEN (dgamma / dbeta may be NULL). */
-size_t mode_batchnorm_workspace_bytes(int C, long long N, long long S);
+size_t mode_batchnorm_workspace_bytes(int C, long long N, long long S, int channels_last);
 int mode_batchnorm_train_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_invstd, float* batch_var,
-                                 float* running_mean, float* running_var, void* workspace, long long N, int C, long long S, float eps, float momentum, void* stream);
+                                 float* running_mean, float* running_var, void* workspace, long long N, int C, long long S, int channels_last, float eps, float momentum,
+                                 void* stream);
 int mode_batchnorm_train_bwd_f32(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd, float* dx, float* dgamma,
-                                 float* dbeta, void* workspace, long long N, int C, long long S, void* stream);
+                                 float* dbeta, void* workspace, long long N, int C, long long S, int channels_last, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,8 +39,8 @@ SIGNATURES = {
     'mode_concat3_nhwc_16': [_vp, _vp, _vp, _vp, C.c_longlong, _i, _i, _i, _vp],
     'mode_disp_to_depth': [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp],
     'mode_grid_sample_border': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    'mode_batchnorm_train_fwd_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, C.c_longlong, _f, _f, _vp],
-    'mode_batchnorm_train_bwd_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, C.c_longlong, _vp],
+    'mode_batchnorm_train_fwd_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, C.c_longlong, _i, _f, _f, _vp],
+    'mode_batchnorm_train_bwd_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, C.c_longlong, _i, _vp],
     'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
 }
 OTHER_SYMBOLS = ['mode_batchnorm_workspace_bytes', 'mode_sphere_conv_table_bytes', 'mode_sphere_conv_backward_workspace_bytes', 'mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
@@ -69,7 +69,7 @@ def load() -> C.CDLL:
     lib.mode_conv3d_packed_weight_elems.argtypes = [_i, _i, _i]
     lib.mode_conv3d_packed_weight_elems.restype = C.c_size_t
   lib.mode_sphere_conv_table_bytes.argtypes = [_i, _i, _i, _i]
-  lib.mode_batchnorm_workspace_bytes.argtypes = [_i, C.c_longlong, C.c_longlong]
+  lib.mode_batchnorm_workspace_bytes.argtypes = [_i, C.c_longlong, C.c_longlong, _i]
   lib.mode_batchnorm_workspace_bytes.restype = C.c_size_t
   lib.mode_sphere_conv_backward_workspace_bytes.argtypes = [_i] * 7
   lib.mode_sphere_conv_backward_workspace_bytes.restype = C.c_size_t

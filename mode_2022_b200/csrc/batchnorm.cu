@@ -83,16 +83,20 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
 
 // ---- forward finalise: mean, biased variance -> save_mean / save_invstd, running statistics (momentum update, unbiased variance)
 __global__ void bn_finalize_kernel(const float* __restrict__ x, const double2* __restrict__ partial, float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                   float* __restrict__ batch_var, float* __restrict__ running_mean, float* __restrict__ running_var, int C, long long S, long long total, int nsplit,
+                                   float* __restrict__ batch_var, float* __restrict__ running_mean, float* __restrict__ running_var, int C, long long kstride, long long total, int nsplit,
                                    float eps, float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel: lanes stride over the channel's partials, then a shuffle tree -- a fixed summation order
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < nsplit; ++i) {
+  for (int i = lane; i < nsplit; i += 32) {
     const double2 p = partial[(size_t)c * nsplit + i];
     s1 += p.x, s2 += p.y;
   }
-  const double K = (double)__ldg(x + (size_t)c * S);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, d), s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  if (lane != 0) return;
+  const double K = (double)__ldg(x + (size_t)c * kstride);  // the shift the partial sums were taken around: x[0, c, 0]
   const double n = (double)total;
   const double m1 = s1 / n;
   const double mean = K + m1;
@@ -155,13 +159,17 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const float* 
 // ---- backward finalise: dbeta = sum dy, dgamma = invstd * sum dy (x - mean); coefficients of dx = ca * dy + cb * (x - mean) + cc
 __global__ void bn_bwd_finalize_kernel(const double2* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ invstd, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ coef, int C, long long total, int nsplit) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per channel: lanes stride over the channel's partials, then a shuffle tree -- a fixed summation order
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < nsplit; ++i) {
+  for (int i = lane; i < nsplit; i += 32) {
     const double2 p = partial[(size_t)c * nsplit + i];
     s1 += p.x, s2 += p.y;
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, d), s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  if (lane != 0) return;
   const double is = (double)invstd[c], g = gamma ? (double)gamma[c] : 1.0, n = (double)total;
   if (dbeta) dbeta[c] = (float)s1;
   if (dgamma) dgamma[c] = (float)(s2 * is);
@@ -193,6 +201,88 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const float* _
   }
 }
 
+// =============================================================================================================================
+// channels-last layout: x is (N, S, C) in memory (torch.channels_last / channels_last_3d), R = N * S rows of C contiguous floats,
+// C % 4 == 0 and C <= 256.  A thread owns one float4 column group (the same one on every row it visits), a block a strided set of
+// rows; coalesced 16-byte accesses, per-channel shifted sums reduced through shared memory into fp64 partials [block][C].
+// =============================================================================================================================
+constexpr int kClMaxC = 256;
+
+template <bool BWD>
+__global__ void __launch_bounds__(kBnThreads) bn_cl_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                                                  double2* __restrict__ partial, int C, long long R) {
+  __shared__ float red[kBnThreads][9];
+  const int G = C >> 2;                       // float4 groups per row
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G, rstep = kBnThreads / G;  // G divides 256 for C in {4, 8, ..., 256} powers of two; else the tail threads idle
+  const bool live = r0 < rstep;
+  // forward: shift K = first row of the tensor; backward: the batch mean
+  const float4 K = BWD ? __ldg(reinterpret_cast<const float4*>(mean) + g) : __ldg(reinterpret_cast<const float4*>(x) + g);
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    for (long long r = (long long)blockIdx.x * rstep + r0; r < R; r += (long long)gridDim.x * rstep) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + g);
+      const float a[4] = {v.x - K.x, v.y - K.y, v.z - K.z, v.w - K.w};
+      if (BWD) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * C) + g);
+        const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s1[i] += dd[i], s2[i] = fmaf(dd[i], a[i], s2[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s1[i] += a[i], s2[i] = fmaf(a[i], a[i], s2[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[threadIdx.x][i] = s1[i], red[threadIdx.x][4 + i] = s2[i];
+  __syncthreads();
+  if (threadIdx.x < C) {  // thread c sums the rstep threads that own channel c (fixed order)
+    const int c = threadIdx.x, gg = c >> 2, i = c & 3;
+    double t1 = 0.0, t2 = 0.0;
+    for (int q = 0; q < rstep; ++q) t1 += (double)red[q * G + gg][i], t2 += (double)red[q * G + gg][4 + i];
+    partial[(size_t)c * gridDim.x + blockIdx.x] = make_double2(t1, t2);
+  }
+}
+
+// y = (x - mean) * a + b   or   dx = ca * dy + cb * (x - mean) + cc; one float4 group per thread, fixed over the grid-stride loop
+template <bool BWD>
+__global__ void __launch_bounds__(kBnThreads) bn_cl_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 const float* __restrict__ coef, float* __restrict__ out, int C, long long R) {
+  const int G = C >> 2;
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G, rstep = kBnThreads / G;
+  if (r0 >= rstep) return;
+  float m[4], a[4], b[4], cc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = 4 * g + i;
+    m[i] = __ldg(mean + c);
+    if (BWD) {
+      a[i] = __ldg(coef + 3 * c), b[i] = __ldg(coef + 3 * c + 1), cc[i] = __ldg(coef + 3 * c + 2);
+    } else {
+      a[i] = __ldg(invstd + c) * (gamma ? __ldg(gamma + c) : 1.f), b[i] = beta ? __ldg(beta + c) : 0.f, cc[i] = 0.f;
+    }
+  }
+  for (long long r = (long long)blockIdx.x * rstep + r0; r < R; r += (long long)gridDim.x * rstep) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + g);
+    float4 o;
+    if (BWD) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * C) + g);
+      o = make_float4(fmaf(a[0], d.x, fmaf(b[0], v.x - m[0], cc[0])), fmaf(a[1], d.y, fmaf(b[1], v.y - m[1], cc[1])), fmaf(a[2], d.z, fmaf(b[2], v.z - m[2], cc[2])),
+                      fmaf(a[3], d.w, fmaf(b[3], v.w - m[3], cc[3])));
+    } else {
+      o = make_float4(fmaf(v.x - m[0], a[0], b[0]), fmaf(v.y - m[1], a[1], b[1]), fmaf(v.z - m[2], a[2], b[2]), fmaf(v.w - m[3], a[3], b[3]));
+    }
+    *(reinterpret_cast<float4*>(out + r * C) + g) = o;
+  }
+}
+
+bool cl_supported(int C) { return C >= 4 && C <= kClMaxC && (C & (C - 1)) == 0; }  // power of two: C/4 groups tile the 256 threads
+int cl_blocks(long long R, int C) {
+  const long long rstep = kBnThreads / (C >> 2);
+  return (int)std::max<long long>(1, std::min<long long>(4LL * kNumSMs, (R + rstep - 1) / rstep));
+}
+
 BnSplit pick_split(int C, long long total, bool vec) {
   // enough blocks to fill the GPU several times over, at least ~8 k elements per block
   long long want = std::max<long long>(1, (8LL * kNumSMs + C - 1) / C);
@@ -216,16 +306,30 @@ void pick_rows(long long rows, long long S, long long& seg, int& nseg) {
 
 }  // namespace
 
-extern "C" size_t mode_batchnorm_workspace_bytes(int C, long long N, long long S) {
-  const BnSplit sp = pick_split(C, N * S, S % 4 == 0);
-  return (size_t)C * sp.nsplit * sizeof(double2) + (size_t)3 * C * sizeof(float);
+extern "C" size_t mode_batchnorm_workspace_bytes(int C, long long N, long long S, int channels_last) {
+  const int nsplit = channels_last ? cl_blocks(N * S, C) : pick_split(C, N * S, S % 4 == 0).nsplit;
+  return (size_t)C * nsplit * sizeof(double2) + (size_t)3 * C * sizeof(float);
 }
 
 extern "C" int mode_batchnorm_train_fwd_f32(const float* x, const float* gamma, const float* beta, float* y, float* save_mean, float* save_invstd, float* batch_var,
-                                            float* running_mean, float* running_var, void* workspace, long long N, int C, long long S, float eps, float momentum, void* stream) {
+                                            float* running_mean, float* running_var, void* workspace, long long N, int C, long long S, int channels_last, float eps, float momentum, void* stream) {
   MODE_CHECK_ARG(x && y && save_mean && save_invstd && workspace, "batchnorm_train_fwd_f32: null pointer");
   MODE_CHECK_ARG(N > 0 && C > 0 && S > 0 && N * C < 2147483647LL, "batchnorm_train_fwd_f32: bad shape");
   const long long total = N * S;
+  if (channels_last) {
+    MODE_CHECK_ARG(cl_supported(C), "batchnorm_train_fwd_f32: channels-last layout needs a power-of-two C in [4, 256] (got %d)", C);
+    MODE_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, "batchnorm_train_fwd_f32: channels-last tensors must be 16-byte aligned");
+    cudaStream_t cs = (cudaStream_t)stream;
+    double2* part = reinterpret_cast<double2*>(workspace);
+    const int nb = cl_blocks(total, C);
+    bn_cl_reduce_kernel<false><<<nb, kBnThreads, 0, cs>>>(x, nullptr, nullptr, part, C, total);
+    MODE_CHECK_LAUNCH("batchnorm_train_fwd_f32 (statistics, channels-last)");
+    bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, cs>>>(x, part, save_mean, save_invstd, batch_var, running_mean, running_var, C, 1, total, nb, eps, momentum);
+    MODE_CHECK_LAUNCH("batchnorm_train_fwd_f32 (finalise)");
+    bn_cl_apply_kernel<false><<<nb, kBnThreads, 0, cs>>>(x, nullptr, gamma, beta, save_mean, save_invstd, nullptr, y, C, total);
+    MODE_CHECK_LAUNCH("batchnorm_train_fwd_f32 (normalise, channels-last)");
+    return MODE_OK;
+  }
   const bool vec = S % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
   const BnSplit sp = pick_split(C, total, S % 4 == 0);
   cudaStream_t s = (cudaStream_t)stream;
@@ -236,7 +340,7 @@ extern "C" int mode_batchnorm_train_fwd_f32(const float* x, const float* gamma, 
   else
     bn_stats_kernel<false><<<g1, kBnThreads, 0, s>>>(x, partial, C, S, total, sp);
   MODE_CHECK_LAUNCH("batchnorm_train_fwd_f32 (statistics)");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(x, partial, save_mean, save_invstd, batch_var, running_mean, running_var, C, S, total, sp.nsplit, eps, momentum);
+  bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, s>>>(x, partial, save_mean, save_invstd, batch_var, running_mean, running_var, C, S, total, sp.nsplit, eps, momentum);  // K = x[c * S]
   MODE_CHECK_LAUNCH("batchnorm_train_fwd_f32 (finalise)");
   long long seg;
   int nseg;
@@ -251,10 +355,26 @@ extern "C" int mode_batchnorm_train_fwd_f32(const float* x, const float* gamma, 
 }
 
 extern "C" int mode_batchnorm_train_bwd_f32(const float* x, const float* dy, const float* gamma, const float* save_mean, const float* save_invstd, float* dx,
-                                            float* dgamma, float* dbeta, void* workspace, long long N, int C, long long S, void* stream) {
+                                            float* dgamma, float* dbeta, void* workspace, long long N, int C, long long S, int channels_last, void* stream) {
   MODE_CHECK_ARG(x && dy && dx && save_mean && save_invstd && workspace, "batchnorm_train_bwd_f32: null pointer");
   MODE_CHECK_ARG(N > 0 && C > 0 && S > 0 && N * C < 2147483647LL, "batchnorm_train_bwd_f32: bad shape");
   const long long total = N * S;
+  if (channels_last) {
+    MODE_CHECK_ARG(cl_supported(C), "batchnorm_train_bwd_f32: channels-last layout needs a power-of-two C in [4, 256] (got %d)", C);
+    MODE_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+                   "batchnorm_train_bwd_f32: channels-last tensors must be 16-byte aligned");
+    cudaStream_t cs = (cudaStream_t)stream;
+    const int nb = cl_blocks(total, C);
+    double2* part = reinterpret_cast<double2*>(workspace);
+    float* cf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + (size_t)C * nb * sizeof(double2));
+    bn_cl_reduce_kernel<true><<<nb, kBnThreads, 0, cs>>>(x, dy, save_mean, part, C, total);
+    MODE_CHECK_LAUNCH("batchnorm_train_bwd_f32 (reductions, channels-last)");
+    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, cs>>>(part, gamma, save_invstd, dgamma, dbeta, cf, C, total, nb);
+    MODE_CHECK_LAUNCH("batchnorm_train_bwd_f32 (finalise)");
+    bn_cl_apply_kernel<true><<<nb, kBnThreads, 0, cs>>>(x, dy, nullptr, nullptr, save_mean, nullptr, cf, dx, C, total);
+    MODE_CHECK_LAUNCH("batchnorm_train_bwd_f32 (dx, channels-last)");
+    return MODE_OK;
+  }
   const bool vec = S % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
   const BnSplit sp = pick_split(C, total, S % 4 == 0);
   cudaStream_t s = (cudaStream_t)stream;
@@ -266,7 +386,7 @@ extern "C" int mode_batchnorm_train_bwd_f32(const float* x, const float* dy, con
   else
     bn_bwd_reduce_kernel<false><<<g1, kBnThreads, 0, s>>>(x, dy, save_mean, partial, C, S, total, sp);
   MODE_CHECK_LAUNCH("batchnorm_train_bwd_f32 (reductions)");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(partial, gamma, save_invstd, dgamma, dbeta, coef, C, total, sp.nsplit);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, s>>>(partial, gamma, save_invstd, dgamma, dbeta, coef, C, total, sp.nsplit);
   MODE_CHECK_LAUNCH("batchnorm_train_bwd_f32 (finalise)");
   long long seg;
   int nseg;

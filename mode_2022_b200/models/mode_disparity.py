@@ -57,6 +57,7 @@ class ModeDisparity(nn.Module):
     super().__init__()
     self.maxdisp = maxdisp
     self.out_conf = out_conf
+    self.train_channels_last = os.environ.get('MODE_B200_TRAIN_CHANNELS_LAST', '1') != '0'  # memory format of the 3-D stack in training (values unchanged)
     self.sphereType = sphereType
     self.precision = precision or os.environ.get('MODE_B200_PRECISION', 'fp16')
     if self.precision not in ('fp32', 'bf16', 'fp16'):
@@ -158,6 +159,11 @@ class ModeDisparity(nn.Module):
     # integer shifts: cost[:, :C, i, :, i:] = ref[..., i:], cost[:, C:, i, :, i:] = tgt[..., :W-i] -- one kernel; its backward is a
     # deterministic gather-sum over the shifts (mode_cost_volume_backward_f32), registered on the op with torch.library
     cost = ops.cost_volume(fl.contiguous(), fr.contiguous(), d4)
+    if self.train_channels_last:
+      # NDHWC for the whole 3-D stack: cuDNN's tensor-core conv3d kernels (fprop / dgrad / wgrad) are NDHWC kernels -- on NCDHW
+      # tensors every call is wrapped in layout transforms (762 of them, 14 ms of a 117 ms step); BatchNorm3d (models/batchnorm.py)
+      # normalises channels-last tensors in place, ReLU and the skip additions keep the format.  Values are unchanged.
+      cost = cost.contiguous(memory_format=torch.channels_last_3d)
     cost0 = self.dres0(cost)
     cost0 = self.dres1(cost0) + cost0
     out1, pre1, post1 = self.dres2(cost0, None, None)

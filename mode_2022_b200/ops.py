@@ -264,30 +264,40 @@ torch.library.register_autograd('mode_b200::disp_regress', _disp_regress_bwd, se
 # ------------------------------------------------------------------------------------------------
 # f1. training-mode BatchNorm (batch statistics)
 # ------------------------------------------------------------------------------------------------
-def _bn_dims(x: torch.Tensor):
+def _bn_layout(x: torch.Tensor, name: str):
+  """(x as the kernels read it, N, C, S, channels_last): a dense channels_last / channels_last_3d tensor with a power-of-two channel
+  count is processed in place as (N, S, C) -- what cuDNN's tensor-core conv kernels produce and consume without layout transforms;
+  everything else as contiguous (N, C, S)."""
+  if not x.is_cuda:
+    raise NotImplementedError(f'{name}: only CUDA tensors are supported (no CPU fallback)')
+  if x.dtype != torch.float32:
+    raise TypeError(f'{name}: expected torch.float32, got {x.dtype}')
   if x.dim() < 3:
-    raise ValueError('batch_norm_train: expected (N, C, spatial...) input')
+    raise ValueError(f'{name}: expected (N, C, spatial...) input')
   n, c = x.shape[0], x.shape[1]
-  return n, c, x.numel() // (n * c)
+  s = x.numel() // (n * c)
+  fmt = torch.channels_last if x.dim() == 4 else torch.channels_last_3d if x.dim() == 5 else None
+  if fmt is not None and not x.is_contiguous() and x.is_contiguous(memory_format=fmt) and 4 <= c <= 256 and (c & (c - 1)) == 0:
+    return x, n, c, s, 1, fmt
+  return x.contiguous(), n, c, s, 0, torch.contiguous_format
 
 
-def _bn_workspace(x: torch.Tensor, n: int, c: int, s: int) -> torch.Tensor:
-  return torch.empty((_lib.load().mode_batchnorm_workspace_bytes(c, n, s) + 15) // 16 * 2, dtype=torch.float64, device=x.device)
+def _bn_workspace(x: torch.Tensor, n: int, c: int, s: int, cl: int) -> torch.Tensor:
+  return torch.empty((_lib.load().mode_batchnorm_workspace_bytes(c, n, s, cl) + 15) // 16 * 2, dtype=torch.float64, device=x.device)
 
 
 @torch.library.custom_op('mode_b200::batch_norm_train', mutates_args=())
 @_device_guard
 def batch_norm_train(x: torch.Tensor, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
   """Training-mode BatchNorm of a (N, C, *spatial) fp32 tensor (nn.BatchNorm2d / 3d as the reference trains them, models/submodule.py:14-30):
-  returns (y, batch mean, 1/sqrt(biased var + eps), unbiased batch variance).  Functional: the module (models/batchnorm.py) applies the
-  momentum update of the running statistics from the returned vectors."""
-  x = _chk(x, torch.float32, 'batch_norm_train')
-  n, c, s = _bn_dims(x)
+  returns (y, batch mean, 1/sqrt(biased var + eps), unbiased batch variance); y keeps x's memory format (contiguous or channels_last).
+  Functional: the module (models/batchnorm.py) applies the momentum update of the running statistics from the returned vectors."""
+  x, n, c, s, cl, _ = _bn_layout(x, 'batch_norm_train')
   weight, bias = _opt(weight, torch.float32, 'batch_norm_train'), _opt(bias, torch.float32, 'batch_norm_train')
-  y = torch.empty_like(x)
+  y = torch.empty_like(x)  # dense input: same strides
   mean, invstd, var_u = x.new_empty(c), x.new_empty(c), x.new_empty(c)
-  ws = _bn_workspace(x, n, c, s)
-  _lib.call('mode_batchnorm_train_fwd_f32', _p(x), _p(weight), _p(bias), _p(y), _p(mean), _p(invstd), _p(var_u), None, None, _p(ws), n, c, s, float(eps), 0.0, _stream())
+  ws = _bn_workspace(x, n, c, s, cl)
+  _lib.call('mode_batchnorm_train_fwd_f32', _p(x), _p(weight), _p(bias), _p(y), _p(mean), _p(invstd), _p(var_u), None, None, _p(ws), n, c, s, cl, float(eps), 0.0, _stream())
   return y, mean, invstd, var_u
 
 
@@ -302,13 +312,15 @@ def _(x, weight, bias, eps):
 def batch_norm_train_backward(x: torch.Tensor, grad_y: torch.Tensor, weight: Optional[torch.Tensor], save_mean: torch.Tensor,
                               save_invstd: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
   """(grad_x, grad_weight, grad_bias) of batch_norm_train."""
-  x, grad_y = _chk(x, torch.float32, 'batch_norm_train_backward'), _chk(grad_y, torch.float32, 'batch_norm_train_backward')
-  n, c, s = _bn_dims(x)
+  x, n, c, s, cl, fmt = _bn_layout(x, 'batch_norm_train_backward')
+  if grad_y.dtype != torch.float32 or grad_y.shape != x.shape:
+    raise TypeError('batch_norm_train_backward: grad_y must be an fp32 tensor of x\'s shape')
+  grad_y = grad_y.contiguous(memory_format=fmt)  # same memory format as x (no copy when the producer already wrote it that way)
   gx = torch.empty_like(x)
   gw, gb = x.new_empty(c), x.new_empty(c)
-  ws = _bn_workspace(x, n, c, s)
+  ws = _bn_workspace(x, n, c, s, cl)
   _lib.call('mode_batchnorm_train_bwd_f32', _p(x), _p(grad_y), _p(_opt(weight, torch.float32, 'batch_norm_train_backward')), _p(save_mean), _p(save_invstd), _p(gx), _p(gw),
-            _p(gb), _p(ws), n, c, s, _stream())
+            _p(gb), _p(ws), n, c, s, cl, _stream())
   return gx, gw, gb
 
 
@@ -327,7 +339,7 @@ def _bn_setup(ctx, inputs, output):
 def _bn_bwd(ctx, grad_y, grad_mean, grad_invstd, grad_var):
   """Gradient through y only: the statistics outputs feed the (non-differentiable) running-stat update."""
   x, weight, mean, invstd = ctx.saved_tensors
-  gx, gw, gb = batch_norm_train_backward(x, grad_y.contiguous(), weight, mean, invstd)
+  gx, gw, gb = batch_norm_train_backward(x, grad_y, weight, mean, invstd)
   return gx, (gw if ctx.has_weight else None), (gb if ctx.has_bias else None), None
 
 

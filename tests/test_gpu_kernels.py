@@ -598,8 +598,9 @@ def test_sphere_conv_backward_is_run_to_run_deterministic(ops):
 
 
 # ---------------------------------------------------------------------------- f1 training-mode BatchNorm
+@pytest.mark.parametrize('cl', [False, True])
 @pytest.mark.parametrize('shape', [(2, 32, 12, 64, 32), (1, 64, 6, 32, 16), (3, 5, 7, 9), (2, 128, 64, 32), (4, 3, 5, 7, 3), (1, 8, 2, 2)])
-def test_batch_norm_train_vs_torch(ops, shape):
+def test_batch_norm_train_vs_torch(ops, shape, cl):
   """mode_b200::batch_norm_train (+ backward) == F.batch_norm(training=True) of torch on the same GPU: output, saved statistics,
   running-stat update (momentum 0.1, unbiased variance), grad_input / grad_weight / grad_bias.  Shapes cover NCHW and NCDHW, vector
   (S % 4 == 0) and scalar paths, a non-zero mean much larger than the spread (shifted-sum statistics)."""
@@ -608,6 +609,9 @@ def test_batch_norm_train_vs_torch(ops, shape):
   C = shape[1]
   x = (torch.randn(*shape, generator=g) * 0.7 + 30.0 * torch.randn(1, C, *([1] * (len(shape) - 2)), generator=g)).cuda()
   gy = torch.randn(*shape, generator=g).cuda()
+  if cl:  # channels_last / channels_last_3d tensors are normalised in place as (N, S, C) when C is a power of two >= 4 (else: contiguous copy)
+    fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+    x, gy = x.contiguous(memory_format=fmt), gy.contiguous(memory_format=fmt)
   cls_t, cls_m = (torch.nn.BatchNorm3d, BatchNorm3d) if len(shape) == 5 else (torch.nn.BatchNorm2d, BatchNorm2d)
   ref, got = cls_t(C).cuda().train(), cls_m(C).cuda().train()
   with torch.no_grad():
@@ -618,6 +622,8 @@ def test_batch_norm_train_vs_torch(ops, shape):
   for _ in range(2):  # two steps: the running statistics accumulate
     yr, yg = ref(xr), got(xg)
   yr.backward(gy), yg.backward(gy)
+  if not cl or (C >= 4 and C & (C - 1) == 0):
+    assert yg.stride() == xg.stride()  # the memory format is kept (channels-last needs a power-of-two C >= 4, else a contiguous copy is normalised)
   x64 = x.double()
   dims = [0] + list(range(2, x.dim()))
   truth = ((x64 - x64.mean(dims, keepdim=True)) / torch.sqrt(x64.var(dims, unbiased=False, keepdim=True) + 1e-5)) * ref.weight.double().view(1, C, *([1] * (x.dim() - 2))) \

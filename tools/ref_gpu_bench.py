@@ -6,7 +6,9 @@
   C. the spherical conv as im2col (torch gather) + cuBLAS 16-bit GEMM, and the GEMM alone (the floor of any un-fused design),
      next to mode_sphere_conv_tc.
 
-    python tools/ref_gpu_bench.py [A] [B] [C]      -> gpurun_out/ref_gpu_bench.json + a table on stdout
+  D. the unmodified reference's TRAINING step (its modules, its op, cuDNN) next to mode_2022_b200.training.train_step.
+
+    python tools/ref_gpu_bench.py [A] [B] [C] [D]  -> gpurun_out/ref_gpu_bench.json + a table on stdout
 """
 import json
 import math
@@ -189,15 +191,69 @@ def part_c(B=12, C=128, Co=128, h=256, w=128):
   OUT['C'] = res
 
 
+def part_d():
+  """The UNMODIFIED reference's training step on the same GPU (train_disparity.py:147-163: three heads, smooth-L1 with weights
+  0.5 / 0.7 / 1.0, Adam), 1 pair 1024x512 D=192, torch defaults (cuDNN TF32 allowed), next to mode_2022_b200.training.train_step."""
+  pkg = SR.reference_package()
+  if pkg is None:
+    OUT['D'] = {'unavailable': 'baseline/_ref/ref not staged'}
+    return
+  from mode_2022_b200 import training as T
+  from mode_2022_b200.models import ModeDisparity
+  torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = True, False
+  g = torch.Generator().manual_seed(1)
+  res = {}
+  for B in (1, 2):
+    left, right = torch.randn(B, 3, H, W, generator=g).cuda(), torch.randn(B, 3, H, W, generator=g).cuda()
+    disp = (torch.rand(B, 1, H, W, generator=g) * (D - 1)).cuda()
+    mask = (torch.rand(B, 1, H, W, generator=g) < 0.9).cuda()
+    sd = O.synthetic_state_dict(Hh.KEY_SHAPES, seed=0)
+    ref = pkg.ModeDisparity(D, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini')
+    ref.load_state_dict(sd)
+    ref = ref.cuda().train()
+    opt_r = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.999))
+
+    def ref_step():
+      opt_r.zero_grad()
+      o1, o2, o3 = ref(left, right)
+      loss = 0.5 * F.smooth_l1_loss(o1[mask], disp[mask], reduction='mean') + 0.7 * F.smooth_l1_loss(o2[mask], disp[mask], reduction='mean') \
+          + F.smooth_l1_loss(o3[mask], disp[mask], reduction='mean')
+      loss.backward()
+      opt_r.step()
+
+    try:
+      torch.cuda.reset_peak_memory_stats()
+      t_ref = ev_time(ref_step, iters=3, warmup=2)
+      mem_ref = torch.cuda.max_memory_allocated() / 2**30
+    except torch.cuda.OutOfMemoryError:
+      t_ref, mem_ref = float('nan'), float('nan')
+    del ref, opt_r
+    torch.cuda.empty_cache()
+    ours = ModeDisparity(D, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', precision='fp32')
+    ours.load_state_dict(sd)
+    ours = ours.cuda().train()
+    red = T.GradAllReduce(ours.parameters())
+    opt_o = torch.optim.Adam(ours.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    torch.cuda.reset_peak_memory_stats()
+    t_ours = ev_time(lambda: T.train_step(ours, red, opt_o, left, right, disp, mask), iters=3, warmup=2)
+    mem_ours = torch.cuda.max_memory_allocated() / 2**30
+    del ours, opt_o, red
+    torch.cuda.empty_cache()
+    res[f'B={B}'] = {'reference_ms': round(t_ref, 1), 'reference_pairs_per_s': round(B / t_ref * 1e3, 2), 'reference_peak_GB': round(mem_ref, 1), 'ours_ms': round(t_ours, 1),
+                     'ours_pairs_per_s': round(B / t_ours * 1e3, 2), 'ours_peak_GB': round(mem_ours, 1), 'speedup': round(t_ref / t_ours, 2)}
+    print(f'[D] training step B={B}: reference {t_ref:.1f} ms ({mem_ref:.1f} GB), ours {t_ours:.1f} ms ({mem_ours:.1f} GB) -> {t_ref / t_ours:.2f}x', flush=True)
+  OUT['D'] = res
+
+
 def main():
-  which = [a for a in sys.argv[1:] if a in ('A', 'B', 'C')] or ['A', 'B', 'C']
+  which = [a for a in sys.argv[1:] if a in ('A', 'B', 'C', 'D')] or ['A', 'B', 'C', 'D']
   t0 = time.time()
   for p in which:
-    {'A': part_a, 'B': part_b, 'C': part_c}[p]()
+    {'A': part_a, 'B': part_b, 'C': part_c, 'D': part_d}[p]()
   OUT['gpu'] = torch.cuda.get_device_name(0)
   OUT['seconds'] = round(time.time() - t0, 1)
   os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-  json.dump(OUT, open(os.path.join(ROOT, 'gpurun_out', 'ref_gpu_bench.json'), 'w'), indent=1)
+  json.dump(OUT, open(os.path.join(ROOT, 'gpurun_out', 'ref_gpu_bench_%s.json' % ''.join(which)), 'w'), indent=1)
 
 
 if __name__ == '__main__':
