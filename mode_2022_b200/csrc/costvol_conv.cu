@@ -30,7 +30,7 @@ namespace {
 // then the D4 x W x 32 outputs of the row are produced from there (each A0 / B0 element is reused ~D4 times; reading them
 // from L2 per output made the kernel L2-read bound at 4x the bytes it writes).  Band / face voxels read UR / UT directly.
 template <int FMT>
-__global__ void __launch_bounds__(256) costvol_conv_kernel(const float* __restrict__ ur, const float* __restrict__ ut, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, 4) costvol_conv_kernel(const float* __restrict__ ur, const float* __restrict__ ut, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, uint16_t* __restrict__ out, int D4, int H, int W, int relu) {
   extern __shared__ __align__(16) float sm[];
   float* a0 = sm;                   // [W][32]
@@ -55,8 +55,11 @@ __global__ void __launch_bounds__(256) costvol_conv_kernel(const float* __restri
           bb.x += v.x, bb.y += v.y, bb.z += v.z, bb.w += v.w;
         }
       }
-    *reinterpret_cast<float4*>(a0 + w * 32 + c4) = a;
-    *reinterpret_cast<float4*>(b0 + w * 32 + c4) = bb;
+    // float4 slot q of row w is stored at slot q ^ (w & 1): the consumer below reads slots 2j and 2j + 1 (j = lane & 3) of two
+    // CONSECUTIVE rows per quarter-warp -- un-swizzled those rows fall on the same banks (row pitch 128 B) and every LDS.128 was a 2-way
+    // conflict (ncu r02: 48 % of this kernel's shared-memory wavefronts)
+    *reinterpret_cast<float4*>(a0 + w * 32 + (c4 ^ ((w & 1) << 2))) = a;
+    *reinterpret_cast<float4*>(b0 + w * 32 + (c4 ^ ((w & 1) << 2))) = bb;
   }
   __syncthreads();
   const int c8 = (threadIdx.x & 3) * 8;  // this thread's 8 output channels (fixed: the loop stride is a multiple of 4)
@@ -64,10 +67,15 @@ __global__ void __launch_bounds__(256) costvol_conv_kernel(const float* __restri
 #pragma unroll
   for (int i = 0; i < 8; ++i) sc[i] = scale ? __ldg(scale + c8 + i) : 1.f, sh[i] = shift ? __ldg(shift + c8 + i) : 0.f;
   const int per_d = W * 4;
-  for (int d = 0; d < D4; ++d) {
-    uint16_t* orow = out + ((((size_t)b * D4 + d) * H + h) * W) * 32;
-    for (int e = threadIdx.x; e < per_d; e += 256) {
-      const int w = e >> 2;
+  // a thread keeps its pixel column w (and 8 channels) and walks the depth axis: A0[w] is depth-independent and stays in registers,
+  // only the B0[w - d] row is read from shared memory per output
+  for (int e = threadIdx.x; e < per_d; e += 256) {
+    const int w = e >> 2;
+    const float4* pa = reinterpret_cast<const float4*>(a0 + w * 32);
+    const int qa = (c8 >> 2) ^ (w & 1);  // swizzled slot of channels c8..c8+3; the next four are slot ^ 1
+    const float4 x0 = pa[qa], x1 = pa[qa ^ 1];
+    for (int d = 0; d < D4; ++d) {
+      uint16_t* orow = out + ((((size_t)b * D4 + d) * H + h) * W) * 32;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -85,9 +93,9 @@ __global__ void __launch_bounds__(256) costvol_conv_kernel(const float* __restri
       };
       if (e_ >= 0) {
         // all nine (kd, kw) terms, as far as A0 / B0 hold them ...
-        const float4* pa = reinterpret_cast<const float4*>(a0 + w * 32 + c8);
-        const float4* pb = reinterpret_cast<const float4*>(b0 + e_ * 32 + c8);
-        const float4 x0 = pa[0], x1 = pa[1], y0 = pb[0], y1 = pb[1];
+        const float4* pb = reinterpret_cast<const float4*>(b0 + e_ * 32);
+        const int qb = (c8 >> 2) ^ (e_ & 1);
+        const float4 y0 = pb[qb], y1 = pb[qb ^ 1];
         acc[0] = x0.x + y0.x, acc[1] = x0.y + y0.y, acc[2] = x0.z + y0.z, acc[3] = x0.w + y0.w;
         acc[4] = x1.x + y1.x, acc[5] = x1.y + y1.y, acc[6] = x1.z + y1.z, acc[7] = x1.w + y1.w;
         // ... minus the ones that are masked at this voxel.  Common cases first (pair index = kd*3 + kw):
