@@ -30,17 +30,23 @@ namespace {
 // then the D4 x W x 32 outputs of the row are produced from there (each A0 / B0 element is reused ~D4 times; reading them
 // from L2 per output made the kernel L2-read bound at 4x the bytes it writes).  Band / face voxels read UR / UT directly.
 template <int FMT>
-__global__ void __launch_bounds__(256, 4) costvol_conv_kernel(const float* __restrict__ ur, const float* __restrict__ ut, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256, 3) costvol_conv_kernel(const float* __restrict__ ur, const float* __restrict__ ut, const float* __restrict__ scale,
                                                            const float* __restrict__ shift, uint16_t* __restrict__ out, int D4, int H, int W, int relu) {
   extern __shared__ __align__(16) float sm[];
-  float* a0 = sm;                   // [W][32]
-  float* b0 = sm + (size_t)W * 32;  // [W][32]
+  float* a0 = sm;                       // [W][32]
+  float* b0 = sm + (size_t)W * 32;      // [W][32]
+  float* a2 = sm + (size_t)W * 64;      // [W][32] A0 without its kd = 2 terms (far depth face)
+  float* b2 = sm + (size_t)W * 96;      // [W][32] B0 without its kd = 2 terms
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const size_t prow = ((size_t)b * H + h) * W;  // pixel index of (b, h, 0)
   // A0[w][o] = sum_{kd,kw} UR[w-1+kw][kd*3+kw][o] (w-1+kw inside the row), B0[u][o] = sum UT[u+kw-kd][kd*3+kw][o]
   for (int e = threadIdx.x; e < W * 8; e += 256) {
     const int w = e >> 3, c4 = (e & 7) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
+    // the kd = 0 terms are masked on the near face (d = 0: d' = -1), the kd = 2 terms on the far face (d = D4-1: d' = D4): keep their
+    // sums, so that the two face planes need no second (DRAM-latency) pass over UR / UT -- ncu r02b: the kernel sat on long-scoreboard
+    // stalls (17 per issue) of exactly those serialised corrections, its L2 hit rate 4 %
+    float4 fa0 = a, fb0 = a, fa2 = a, fb2 = a;
 #pragma unroll
     for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
@@ -49,12 +55,30 @@ __global__ void __launch_bounds__(256, 4) costvol_conv_kernel(const float* __res
         if (wa >= 0 && wa < W) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(ur + ((prow + wa) * 9 + kd * 3 + kw) * 32 + c4));
           a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+          if (kd == 0) fa0.x += v.x, fa0.y += v.y, fa0.z += v.z, fa0.w += v.w;
+          if (kd == 2) fa2.x += v.x, fa2.y += v.y, fa2.z += v.z, fa2.w += v.w;
         }
         if (wb >= 0 && wb < W) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(ut + ((prow + wb) * 9 + kd * 3 + kw) * 32 + c4));
           bb.x += v.x, bb.y += v.y, bb.z += v.z, bb.w += v.w;
+          if (kd == 0) fb0.x += v.x, fb0.y += v.y, fb0.z += v.z, fb0.w += v.w;
+          if (kd == 2) fb2.x += v.x, fb2.y += v.y, fb2.z += v.z, fb2.w += v.w;
         }
       }
+    // far face (d = D4-1), consumed below from shared memory: A-side and B-side sums without their kd = 2 terms
+    *reinterpret_cast<float4*>(a2 + w * 32 + (c4 ^ ((w & 1) << 2))) = make_float4(a.x - fa2.x, a.y - fa2.y, a.z - fa2.z, a.w - fa2.w);
+    *reinterpret_cast<float4*>(b2 + w * 32 + (c4 ^ ((w & 1) << 2))) = make_float4(bb.x - fb2.x, bb.y - fb2.y, bb.z - fb2.z, bb.w - fb2.w);
+    // near face (d = 0, e = w: both sums belong to this thread): out = A0[w] + B0[w] - (kd = 0 terms); for 2 <= w <= W-2 nothing else
+    // is masked there (d' = kd - 1 <= 1 <= w' and every column is inside the row)
+    if (D4 >= 2 && w >= 2 && w <= W - 2) {
+      float y[4] = {(a.x + bb.x) - (fa0.x + fb0.x), (a.y + bb.y) - (fa0.y + fb0.y), (a.z + bb.z) - (fa0.z + fb0.z), (a.w + bb.w) - (fa0.w + fb0.w)};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        y[i] = fmaf(y[i], scale ? __ldg(scale + c4 + i) : 1.f, shift ? __ldg(shift + c4 + i) : 0.f);
+        y[i] = relu ? fmaxf(y[i], 0.f) : y[i];
+      }
+      *reinterpret_cast<uint2*>(out + ((((size_t)b * D4) * H + h) * W + w) * 32 + c4) = make_uint2(pack2<FMT>(y[0], y[1]), pack2<FMT>(y[2], y[3]));
+    }
     // float4 slot q of row w is stored at slot q ^ (w & 1): the consumer below reads slots 2j and 2j + 1 (j = lane & 3) of two
     // CONSECUTIVE rows per quarter-warp -- un-swizzled those rows fall on the same banks (row pitch 128 B) and every LDS.128 was a 2-way
     // conflict (ncu r02: 48 % of this kernel's shared-memory wavefronts)
@@ -74,12 +98,23 @@ __global__ void __launch_bounds__(256, 4) costvol_conv_kernel(const float* __res
     const float4* pa = reinterpret_cast<const float4*>(a0 + w * 32);
     const int qa = (c8 >> 2) ^ (w & 1);  // swizzled slot of channels c8..c8+3; the next four are slot ^ 1
     const float4 x0 = pa[qa], x1 = pa[qa ^ 1];
-    for (int d = 0; d < D4; ++d) {
+    const bool near_done = D4 >= 2 && w >= 2 && w <= W - 2;  // d = 0 was written by the reduction pass above
+    for (int d = near_done ? 1 : 0; d < D4; ++d) {
       uint16_t* orow = out + ((((size_t)b * D4 + d) * H + h) * W) * 32;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
       const int e_ = w - d;
+      const bool far_fast = d == D4 - 1 && d >= 2 && e_ >= 2 && w <= W - 2;
+      if (far_fast) {
+        // far face away from the diagonal and the row ends: only the kd = 2 terms (d' = D4) are masked
+        const float4* pa2 = reinterpret_cast<const float4*>(a2 + w * 32);
+        const float4* pb2 = reinterpret_cast<const float4*>(b2 + e_ * 32);
+        const int qb = (c8 >> 2) ^ (e_ & 1);
+        const float4 u0 = pa2[qa], u1 = pa2[qa ^ 1], y0 = pb2[qb], y1 = pb2[qb ^ 1];
+        acc[0] = u0.x + y0.x, acc[1] = u0.y + y0.y, acc[2] = u0.z + y0.z, acc[3] = u0.w + y0.w;
+        acc[4] = u1.x + y1.x, acc[5] = u1.y + y1.y, acc[6] = u1.z + y1.z, acc[7] = u1.w + y1.w;
+      }
       const bool mid = d >= 1 && d <= D4 - 2 && w >= 1;  // no depth-face term, w-1 inside the row
       auto sub8 = [&](const float* base, size_t pix, int kdkw) {
         const float4* q = reinterpret_cast<const float4*>(base + (pix * 9 + kdkw) * 32 + c8);
@@ -91,7 +126,9 @@ __global__ void __launch_bounds__(256, 4) costvol_conv_kernel(const float* __res
         const float4 z0 = __ldg(q), z1 = __ldg(q + 1);
         acc[0] += z0.x, acc[1] += z0.y, acc[2] += z0.z, acc[3] += z0.w, acc[4] += z1.x, acc[5] += z1.y, acc[6] += z1.z, acc[7] += z1.w;
       };
-      if (e_ >= 0) {
+      if (far_fast) {
+        // done above
+      } else if (e_ >= 0) {
         // all nine (kd, kw) terms, as far as A0 / B0 hold them ...
         const float4* pb = reinterpret_cast<const float4*>(b0 + e_ * 32);
         const int qb = (c8 >> 2) ^ (e_ & 1);
@@ -179,7 +216,7 @@ extern "C" int mode_costvol_conv_fused(const float* ur, const float* ut, const f
   MODE_CHECK_ARG(fmt == kFmtBF16 || fmt == kFmtFP16, "costvol_conv_fused: fmt must be 0 (bf16) or 1 (fp16)");
   MODE_CHECK_ARG(ur && ut && out, "costvol_conv_fused: null pointer");
   MODE_CHECK_ARG(B > 0 && D4 > 0 && H > 0 && W > 0, "costvol_conv_fused: bad shape");
-  const size_t smem = (size_t)2 * W * 32 * sizeof(float);
+  const size_t smem = (size_t)4 * W * 32 * sizeof(float);
   MODE_CHECK_ARG(smem <= 200 * 1024, "costvol_conv_fused: feature map too wide (W = %d)", W);
   static thread_local size_t attr_dev[kMaxDevices] = {};  // the attribute is per device and per function
   size_t& attr = attr_dev[current_device()];
