@@ -324,3 +324,35 @@ def test_fusion_stage_graph_matches_eager():
     assert got.shape == (1, 1, H, W) and torch.equal(got, want)
     got2 = st(disp * 0.5, conf, rgbs)  # replay with new inputs
     assert not torch.equal(got2, want)
+
+
+def test_full_size_forward_is_run_to_run_identical_eager_and_graph():
+  """1024x512, D=192, 2 pairs, fp16 plan: the forward is bit-identical from run to run, eager and replayed from a CUDA graph.  The
+  spherical layers launch their second kernel under the first one's tail (programmatic stream serialization, csrc/sphere_conv_tc.cu):
+  a missing dependency there (a kernel reading the previous layer's output too early) would show up here as run-to-run differences."""
+  from mode_2022_b200.models import ModeDisparity
+  m = ModeDisparity(192, in_height=1024, in_width=512, sphereType='Cassini', out_conf=True, precision='fp16')
+  m.load_state_dict(O.synthetic_state_dict(Hh.KEY_SHAPES, seed=0))  # un-saturated in eval mode without a calibration pass
+  m = m.cuda().eval()
+  g = torch.Generator().manual_seed(4)
+  left, right = torch.randn(2, 3, 1024, 512, generator=g).cuda(), torch.randn(2, 3, 1024, 512, generator=g).cuda()
+  with torch.no_grad():
+    p0, c0 = m(left, right)
+    p0, c0 = p0.clone(), c0.clone()
+    assert torch.isfinite(p0).all() and torch.isfinite(c0).all()
+    for _ in range(6):
+      p, c = m(left, right)
+      assert torch.equal(p, p0) and torch.equal(c, c0)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      m(left, right)  # warm-up on the capture stream
+      with torch.cuda.graph(graph, stream=side):
+        pg, cg = m(left, right)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(6):
+      graph.replay()
+      torch.cuda.synchronize()
+      assert torch.equal(pg, p0) and torch.equal(cg, c0)

@@ -124,3 +124,4 @@ def test_reference_python_runs_on_libmode_b200_shim(ref_pkg):
   # the shim reports errors the way the C ABI does (the reference op would TORCH_CHECK): stride 2 is not built
   with pytest.raises(RuntimeError):
     shim.sphere_conv_forward_cuda(x, torch.empty(8, 64, 3, 3).cuda(), x, x, x, x, x, 3, 3, 2, 2, 1, 1, 1, 1, 1, False)
+

@@ -67,9 +67,13 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_active.avg', 'dram__bytes_read.sum
 
 def full(rep, title, out):
   path = os.path.join(OUT, rep)
-  if not os.path.exists(path):
+  raw = path.replace('.ncu-rep', '.raw.csv')  # exported on the GPU box (tools/collect_profiles_r02b.sh), the report itself stays there
+  if os.path.exists(raw):
+    txt = open(raw).read()
+  elif os.path.exists(path):
+    txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+  else:
     return
-  txt = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
   r = list(csv.reader(txt.splitlines()))
   h, u, v = r[0], r[1], r[2]
   d = {a.split('TriageCompute.')[-1]: (b, c) for a, b, c in zip(h, u, v)}  # some metrics carry a '<unit>.TriageCompute.' prefix
@@ -87,12 +91,16 @@ R02 = [('r02_sphere_slab.ncu-rep', 'sphere_conv_slab_kernel<fp16, cassini> 128->
        ('r02_conv3d_s2small.ncu-rep', 'conv3d_tc_kernel<1,..> 64->64 stride 2 @24x128x64 -> 12x64x32, B=6 (small-grid tail)', 'conv3d_tc_s2_small_ncu.md'),
        ('r02_cls.ncu-rep', 'conv3d_cls_tc_kernel<fp16> 32->1 classifier, B=6, 48x256x128', 'conv3d_cls_tc_ncu.md'),
        ('r02_costvol.ncu-rep', 'costvol_conv_kernel<fp16> cost volume fused into dres0[0], B=6, 256x128 features, D/4=48', 'costvol_conv_ncu.md'),
-       ('r02_regress.ncu-rep', 'disp_regress_kernel<48,192> upsample + softmax + soft-argmin + confidence, 1 pair 1024x512', 'disp_regress_ncu.md'),
+       ('r02_regress.ncu-rep', 'disp_regress_192_kernel (row-tile kernel) upsample + softmax + soft-argmin + confidence, 1 pair 1024x512', 'disp_regress_ncu.md'),
        ('r02_cost_volume.ncu-rep', 'cost_volume_bf16_kernel (stand-alone 16-bit NDHWC cost volume), 1 pair', 'cost_volume_ncu.md'),
        ('r02_stem.ncu-rep', 'stem_conv_tc_kernel<fp16> 3->32 7x7 s2 @1024x512, B=12', 'stem_conv_tc_ncu.md'),
        ('r02_warp.ncu-rep', 'warp_scatter_kernel (z-buffer forward warp, pass 0), 1024x512', 'geometry_warp_ncu.md'),
-       ('r02_sphere_dgrad.ncu-rep', 'sphere_dgrad_f32_kernel<deterministic> (training, 512x256 D=96 B=2)', 'sphere_dgrad_ncu.md'),
-       ('r02_sphere_wgrad.ncu-rep', 'sphere_wgrad_f32_kernel<deterministic> (training)', 'sphere_wgrad_ncu.md'),
+       ('r02_sphere_f32.ncu-rep', 'sphere_conv_f32_tiled_kernel (training / fp32 parity forward: register-tiled SGEMM with fused gather; 512x256 D=96 B=2)', 'sphere_f32_fwd_ncu.md'),
+       ('r02_sphere_dgrad.ncu-rep', 'sphere_dgrad_f32_tiled_kernel<deterministic> (training, 512x256 D=96 B=2)', 'sphere_dgrad_ncu.md'),
+       ('r02_sphere_wgrad.ncu-rep', 'sphere_wgrad_f32_tiled_kernel<deterministic> (training)', 'sphere_wgrad_ncu.md'),
+       ('r02_bn_cl_reduce.ncu-rep', 'bn_cl_reduce_kernel (training BatchNorm3d, channels-last: per-channel sums)', 'bn_cl_reduce_ncu.md'),
+       ('r02_bn_cl_apply.ncu-rep', 'bn_cl_apply_kernel (training BatchNorm3d, channels-last: normalise / dx)', 'bn_cl_apply_ncu.md'),
+       ('r02_bn_bwd_apply.ncu-rep', 'bn_bwd_apply_kernel (training BatchNorm2d backward, NCHW: dx)', 'bn_bwd_apply_ncu.md'),
        ('r02_regress_bwd.ncu-rep', 'disp_regress_bwd_kernel (training: fused soft-argmin head backward)', 'disp_regress_bwd_ncu.md'),
        ('r02_cost_volume_bwd.ncu-rep', 'cost_volume_bwd_f32_kernel (training: gather-sum over the shifts)', 'cost_volume_bwd_ncu.md')]
 
@@ -117,6 +125,17 @@ if __name__ == '__main__':
     if os.path.exists(os.path.join(OUT, f)):
       keep = [l for l in open(os.path.join(OUT, f)) if l.startswith(('{', 'conv3d_tc', 'sphere_conv_tc', 'direct-gather', 'pointwise', 'implicit-gemm', 'fused', 'cost_volume +'))]
       open(os.path.join(PROF, o), 'w').write(''.join(keep))
+  for f, o in ((f'{TAG}_train_profile.txt', f'{TAG}_train_profile.txt'), (f'{TAG}_ref_train.txt', f'{TAG}_reference_train_step.txt'), (f'{TAG}_mufu_bench.txt', f'{TAG}_mufu_microbench.txt'),
+               (f'{TAG}_sphere_split.txt', f'{TAG}_sphere_kernel_split.txt')):
+    if os.path.exists(os.path.join(OUT, f)):
+      keep = [l for l in open(os.path.join(OUT, f)) if 'Warn' not in l and 'warn' not in l and l.strip()]
+      open(os.path.join(PROF, o), 'w').write(''.join(keep))
+  for mode in ('train', 'twostage', 'highres'):
+    f = os.path.join(OUT, f'{TAG}_bench_{mode}.json')
+    if os.path.exists(f):
+      lines = [l for l in open(f) if l.startswith('{')]
+      if lines:
+        open(os.path.join(PROF, f'{TAG}_bench_line_{mode}.json'), 'w').write(lines[-1])
   if os.path.exists(os.path.join(OUT, final)):
     line = [l for l in open(os.path.join(OUT, final)) if l.startswith('{')][-1]
     open(os.path.join(PROF, f'{TAG}_bench_line.json'), 'w').write(line)
