@@ -111,7 +111,7 @@ def build_model(device, precision=None):
   return m.to(device).eval()
 
 
-MUFU_EXP_PER_S = 148 * 16 * 1.965e9  # SFU exp2 rate: 148 SMs x 16 lanes/clk x max SM clock
+MUFU_EXP_PER_S = 148 * 16 * 1.965e9  # SFU exp2 rate: 148 SMs x 16 lanes/clk x max SM clock; measured 15.9 lanes/clk/SM = 4.63 T/s (tools/mufu_bench.cu, profiles/r02_mufu_microbench.txt)
 
 
 def _cval(a):
@@ -202,7 +202,7 @@ def roofline_report(prof, reps):
           'achieved': round(ach, 1), 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': round(ach / pk['bf16_tflops_sustained'], 3),
           'traffic': CONV3D_DRAM_BYTES_PER_STEP,
           'traffic_note': 'DRAM read+write bytes of the conv3d launches of one step (6 pairs), ncu launch list under profiles/',
-          'peak_source': pk['source'] + ' (sustained 16-bit dense; burst %.0f; HBM %.1f GB/s; MUFU exp %.2f T/s nominal)' % (pk['bf16_tflops'], pk['hbm_gbs'], MUFU_EXP_PER_S / 1e12),
+          'peak_source': pk['source'] + ' (sustained 16-bit dense; burst %.0f; HBM %.1f GB/s; MUFU exp %.2f T/s nominal, 4.63 measured)' % (pk['bf16_tflops'], pk['hbm_gbs'], MUFU_EXP_PER_S / 1e12),
           'launches_per_step': n_conv, 'ms_per_step_in_kernel': round(t_conv, 3),
           'kernels': kernels}
 
