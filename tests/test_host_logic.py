@@ -110,3 +110,25 @@ def test_bench_roofline_report_classes():
   assert by['conv3d_tc 64->32 deconv @24x128x64']['bound'] == 'hbm'           # 1.3 GB moved: HBM-bound, not tensor-bound
   assert by['disp_regress (upsample + softmax + soft-argmin + confidence)']['bound'] == 'mufu_exp'
   assert by['sphere_conv_tc 128->128 @256x128']['launches_per_step'] == 1
+
+
+def test_batchnorm_modules_are_drop_in_on_the_host():
+  """models/batchnorm.py: same parameters, buffers and state-dict keys as torch's modules, `isinstance` still holds (the reference's
+  init code and the BN-folding plans test for nn.BatchNorm2d / 3d), and everything the CUDA kernels do not cover -- here: CPU tensors,
+  eval mode, momentum=None -- goes through the parent class unchanged.  The kernels themselves are pinned in tests/test_gpu_kernels.py."""
+  import torch.nn as nn
+  from mode_2022_b200.models.batchnorm import BatchNorm2d, BatchNorm3d
+  from mode_2022_b200.models import ModeDisparity
+  for cls_m, cls_t, shape in ((BatchNorm2d, nn.BatchNorm2d, (2, 6, 5, 7)), (BatchNorm3d, nn.BatchNorm3d, (2, 4, 3, 5, 6))):
+    a, b = cls_m(shape[1]), cls_t(shape[1])
+    assert isinstance(a, cls_t) and list(a.state_dict()) == list(b.state_dict())
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(*shape)
+    for mode in ('train', 'train_cumulative', 'eval'):
+      a.train(mode != 'eval'), b.train(mode != 'eval')
+      a.momentum = b.momentum = None if mode == 'train_cumulative' else 0.1
+      assert torch.equal(a(x), b(x))
+      assert torch.equal(a.running_mean, b.running_mean) and torch.equal(a.running_var, b.running_var) and int(a.num_batches_tracked) == int(b.num_batches_tracked)
+  m = ModeDisparity(32, in_height=64, in_width=32, sphereType='Cassini')
+  bns = [mod for mod in m.modules() if isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm3d))]
+  assert bns and all(isinstance(mod, (BatchNorm2d, BatchNorm3d)) for mod in bns)
