@@ -78,6 +78,12 @@ int mode_disp_regress(const float* cost, float* pred, float* conf, int B, int D4
  * (B,D,H,W) volumes per head).  grad_pred (B,H,W) -> grad_cost (B,D4,H4,W4), overwritten (zero-filled by the call); the softmax
  * statistics are recomputed from `cost`, nothing else is saved by the forward.  fp32 atomics (like ATen's upsample backward). */
 int mode_disp_regress_backward(const float* cost, const float* grad_pred, float* grad_cost, int B, int D4, int H4, int W4, int D, int H, int W, void* stream);
+/* the same with a caller-allocated workspace of mode_disp_regress_backward_workspace_bytes() bytes (0 = this shape has no workspace path;
+ * workspace may then be NULL and the call is mode_disp_regress_backward): dL/dt of every full-resolution pixel goes through the workspace
+ * and the bilinear transpose is a gather -- no atomics, bit-identical from run to run. */
+size_t mode_disp_regress_backward_workspace_bytes(int B, int D4, int H4, int W4, int D, int H, int W);
+int mode_disp_regress_backward_ws(const float* cost, const float* grad_pred, float* grad_cost, void* workspace, int B, int D4, int H4, int W4, int D, int H, int W,
+                                  void* stream);
 
 /* ---- a2. spherical convolution forward ----------------------------------------------------------
  * replaces sphere_conv_forward_cuda (sphere_conv_cuda.cpp:129-210) = sphere_im2col_gpu_kernel

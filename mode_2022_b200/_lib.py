@@ -25,6 +25,7 @@ SIGNATURES = {
     'mode_stem_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     'mode_disp_regress': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_disp_regress_backward': [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'mode_disp_regress_backward_ws': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_tc': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     'mode_sphere_conv_pack_weights': [_vp, _vp, _i, _i, _i, _vp],
@@ -43,7 +44,7 @@ SIGNATURES = {
     'mode_batchnorm_train_bwd_f32': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_longlong, _i, C.c_longlong, _i, _vp],
     'mode_depth_view_trans': [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _vp, _vp, _vp, _i, _i, _i, _vp],
 }
-OTHER_SYMBOLS = ['mode_batchnorm_workspace_bytes', 'mode_sphere_conv_table_bytes', 'mode_sphere_conv_backward_workspace_bytes', 'mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
+OTHER_SYMBOLS = ['mode_disp_regress_backward_workspace_bytes', 'mode_batchnorm_workspace_bytes', 'mode_sphere_conv_table_bytes', 'mode_sphere_conv_backward_workspace_bytes', 'mode_conv3d_set_debug_buffer', 'mode_b200_version', 'mode_b200_last_error', 'mode_b200_launch_count', 'mode_conv3d_packed_weight_elems']
 
 PENDING = set()
 _lib = None
@@ -69,6 +70,8 @@ def load() -> C.CDLL:
     lib.mode_conv3d_packed_weight_elems.argtypes = [_i, _i, _i]
     lib.mode_conv3d_packed_weight_elems.restype = C.c_size_t
   lib.mode_sphere_conv_table_bytes.argtypes = [_i, _i, _i, _i]
+  lib.mode_disp_regress_backward_workspace_bytes.argtypes = [_i] * 7
+  lib.mode_disp_regress_backward_workspace_bytes.restype = C.c_size_t
   lib.mode_batchnorm_workspace_bytes.argtypes = [_i, C.c_longlong, C.c_longlong, _i]
   lib.mode_batchnorm_workspace_bytes.restype = C.c_size_t
   lib.mode_sphere_conv_backward_workspace_bytes.argtypes = [_i] * 7

@@ -331,3 +331,145 @@ extern "C" int mode_disp_regress_backward(const float* cost, const float* grad_p
   MODE_CHECK_LAUNCH("disp_regress_backward");
   return MODE_OK;
 }
+
+// ---- backward, maxdisp 192 / width % 256 == 0: two deterministic passes instead of shared + global fp32 atomics.
+//   pass 1 (row-tile kernel, as the forward): a pixel's 48 coarse logits and their gradients live in registers (compile-time indices);
+//           dL/dt[48] of every full-resolution pixel goes to a (B, 48, H, W) workspace, coalesced along w;
+//   pass 2: the transpose of the (h, w) bilinear as a GATHER -- a block owns one coarse row of one plane, first folds the ~11 fine rows
+//           that touch it into a row buffer (weights lh0 / lh1 of the rows whose h0 / h1 is this coarse row), then every coarse column sums
+//           its <= 11 fine columns.  Fixed summation order: the gradient is bit-identical from run to run (the atomics version is not).
+__global__ void __launch_bounds__(kRegThreads, 1) disp_regress_bwd192_pix_kernel(const float* __restrict__ cost, const float* __restrict__ gpred, float* __restrict__ gt_ws,
+                                                                                 int H4, int W4, int H, int W, float sh, float sw) {
+  constexpr int D4 = 48, D = 192;
+  constexpr float sd = (float)(D4 - 1) / (float)(D - 1);
+  constexpr float kLog2e = 1.4426950408889634f;
+  __shared__ float tile[D4][kTileCols];
+  const int wblks = W / kRegThreads;
+  const int h = blockIdx.x / wblks, wb = (blockIdx.x - h * wblks) * kRegThreads;
+  const int b = blockIdx.y;
+  const float hs = sh * h;
+  const int h0 = (int)hs;
+  const int h1 = h0 + (h0 < H4 - 1);
+  const float lh1 = hs - h0, lh0 = 1.f - lh1;
+  const int c_lo = (int)(sw * wb);
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* r0 = cost + ((size_t)b * D4 * H4 + h0) * W4;
+    const float* r1 = cost + ((size_t)b * D4 * H4 + h1) * W4;
+    const int g0 = min(c_lo + lane, W4 - 1), g1 = min(c_lo + lane + 32, W4 - 1), g2 = min(c_lo + lane + 64, W4 - 1);
+#pragma unroll
+    for (int j = 0; j < D4 / 8; ++j) {
+      const int d4 = warp + 8 * j;
+      const size_t po = (size_t)d4 * H4 * W4;
+      tile[d4][lane] = lh0 * __ldg(r0 + po + g0) + lh1 * __ldg(r1 + po + g0);
+      tile[d4][lane + 32] = lh0 * __ldg(r0 + po + g1) + lh1 * __ldg(r1 + po + g1);
+      if (lane < kTileCols - 64) tile[d4][lane + 64] = lh0 * __ldg(r0 + po + g2) + lh1 * __ldg(r1 + po + g2);
+    }
+  }
+  __syncthreads();
+  const int w = wb + threadIdx.x;
+  const float ws = sw * w;
+  const int w0 = (int)ws;
+  const int w1 = w0 + (w0 < W4 - 1);
+  const float lw1 = ws - w0, lw0 = 1.f - lw1;
+  const int i0 = w0 - c_lo, i1 = w1 - c_lo;
+  float t[D4], gt[D4];
+  float m = -INFINITY;
+#pragma unroll
+  for (int d4 = 0; d4 < D4; ++d4) {
+    t[d4] = lw0 * tile[d4][i0] + lw1 * tile[d4][i1];
+    m = fmaxf(m, t[d4]);
+    gt[d4] = 0.f;
+  }
+  const float mneg = -m * kLog2e;
+#pragma unroll
+  for (int d4 = 0; d4 < D4; ++d4) t[d4] = fmaf(t[d4], kLog2e, mneg);
+  float sum = 0.f, wsum = 0.f;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float ds = sd * d;
+    const int d0 = (int)ds;
+    const int d1 = d0 + (d0 < D4 - 1);
+    const float l1 = ds - d0;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l1, t[d1] - t[d0], t[d0])));
+    sum += e;
+    wsum = fmaf(e, (float)d, wsum);
+  }
+  const float pr = wsum / sum;
+  const float g = __ldg(gpred + ((size_t)b * H + h) * W + w) / sum;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float ds = sd * d;
+    const int d0 = (int)ds;
+    const int d1 = d0 + (d0 < D4 - 1);
+    const float l1 = ds - d0, l0 = 1.f - l1;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l1, t[d1] - t[d0], t[d0])));
+    const float gu = g * e * ((float)d - pr);  // dL/du_d = g p_d (d - pred)
+    gt[d0] = fmaf(l0, gu, gt[d0]);
+    gt[d1] = fmaf(l1, gu, gt[d1]);
+  }
+  float* o = gt_ws + (((size_t)b * D4) * H + h) * W + w;
+#pragma unroll
+  for (int d4 = 0; d4 < D4; ++d4) o[(size_t)d4 * H * W] = gt[d4];
+}
+
+__global__ void __launch_bounds__(kRegThreads) disp_regress_bwd192_gather_kernel(const float* __restrict__ gt_ws, float* __restrict__ gcost, int D4, int H4, int W4, int H,
+                                                                                 int W, float sh, float sw) {
+  extern __shared__ float rowbuf[];  // [W] fine columns of this (plane, coarse row), rows already folded
+  const int hc = blockIdx.x, d4 = blockIdx.y, b = blockIdx.z;
+  const float* src = gt_ws + (((size_t)b * D4 + d4) * H) * W;
+  // fine rows whose bilinear footprint includes coarse row hc: h0 == hc (weight lh0) and / or h1 == hc (weight lh1)
+  // candidates: sh * h in (hc - 1, hc + 1), one row of slack on both sides (the exact membership test is repeated per row below)
+  const int hlo = max(0, (int)floorf((hc - 1) / sh) - 1), hhi = min(H - 1, (int)ceilf((hc + 1) / sh) + 1);
+  for (int w = threadIdx.x; w < W; w += kRegThreads) {
+    float acc = 0.f;
+    for (int h = hlo; h <= hhi; ++h) {
+      const float hs = sh * h;
+      const int h0 = (int)hs;
+      const int h1 = h0 + (h0 < H4 - 1);
+      const float lh1 = hs - h0, lh0 = 1.f - lh1;
+      const float wgt = (h0 == hc ? lh0 : 0.f) + (h1 == hc ? lh1 : 0.f);
+      if (wgt != 0.f) acc = fmaf(wgt, __ldg(src + (size_t)h * W + w), acc);
+    }
+    rowbuf[w] = acc;
+  }
+  __syncthreads();
+  for (int wc = threadIdx.x; wc < W4; wc += kRegThreads) {
+    const int wlo = max(0, (int)floorf((wc - 1) / sw) - 1), whi = min(W - 1, (int)ceilf((wc + 1) / sw) + 1);
+    float acc = 0.f;
+    for (int w = wlo; w <= whi; ++w) {
+      const float ws = sw * w;
+      const int w0 = (int)ws;
+      const int w1 = w0 + (w0 < W4 - 1);
+      const float lw1 = ws - w0, lw0 = 1.f - lw1;
+      const float wgt = (w0 == wc ? lw0 : 0.f) + (w1 == wc ? lw1 : 0.f);
+      acc = fmaf(wgt, rowbuf[w], acc);
+    }
+    gcost[(((size_t)b * D4 + d4) * H4 + hc) * W4 + wc] = acc;
+  }
+}
+
+extern "C" size_t mode_disp_regress_backward_workspace_bytes(int B, int D4, int H4, int W4, int D, int H, int W) {
+  const bool fast = D4 == 48 && D == 192 && W % kRegThreads == 0 && W4 * 4 == W && H4 * 4 == H && W4 >= 2 && H4 >= 2;
+  return fast ? (size_t)B * D4 * H * W * sizeof(float) : 0;
+}
+
+extern "C" int mode_disp_regress_backward_ws(const float* cost, const float* grad_pred, float* grad_cost, void* workspace, int B, int D4, int H4, int W4, int D, int H, int W,
+                                             void* stream) {
+  MODE_CHECK_ARG(cost && grad_pred && grad_cost, "disp_regress_backward_ws: null pointer");
+  if (workspace == nullptr || mode_disp_regress_backward_workspace_bytes(B, D4, H4, W4, D, H, W) == 0)
+    return mode_disp_regress_backward(cost, grad_pred, grad_cost, B, D4, H4, W4, D, H, W, stream);
+  MODE_CHECK_ARG(B > 0 && B < 65536, "disp_regress_backward_ws: bad batch");
+  const float sh = (float)(H4 - 1) / (float)(H - 1), sw = (float)(W4 - 1) / (float)(W - 1);
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 g1((unsigned)((long long)H * (W / kRegThreads)), B);
+  disp_regress_bwd192_pix_kernel<<<g1, kRegThreads, 0, s>>>(cost, grad_pred, (float*)workspace, H4, W4, H, W, sh, sw);
+  MODE_CHECK_LAUNCH("disp_regress_backward_ws (per-pixel)");
+  dim3 g2(H4, D4, B);
+  disp_regress_bwd192_gather_kernel<<<g2, kRegThreads, (size_t)W * sizeof(float), s>>>((const float*)workspace, grad_cost, D4, H4, W4, H, W, sh, sw);
+  MODE_CHECK_LAUNCH("disp_regress_backward_ws (gather)");
+  return MODE_OK;
+}
+

@@ -233,7 +233,12 @@ def disp_regress_backward(cost: torch.Tensor, grad_pred: torch.Tensor, maxdisp: 
   if grad_pred.numel() != B * H * W:
     raise ValueError('disp_regress_backward: grad_pred must be (B,1,H,W)')
   gcost = torch.empty_like(cost)
-  _lib.call('mode_disp_regress_backward', _p(cost), _p(grad_pred), _p(gcost), B, D4, H4, W4, maxdisp, H, W, _stream())
+  nws = _lib.load().mode_disp_regress_backward_workspace_bytes(B, D4, H4, W4, maxdisp, H, W)
+  if nws:  # deterministic two-pass path (maxdisp 192, width % 256 == 0): per-pixel dL/dt through a workspace, gather transpose
+    ws = torch.empty(nws // 4, dtype=torch.float32, device=cost.device)
+    _lib.call('mode_disp_regress_backward_ws', _p(cost), _p(grad_pred), _p(gcost), _p(ws), B, D4, H4, W4, maxdisp, H, W, _stream())
+  else:
+    _lib.call('mode_disp_regress_backward', _p(cost), _p(grad_pred), _p(gcost), B, D4, H4, W4, maxdisp, H, W, _stream())
   return gcost
 
 

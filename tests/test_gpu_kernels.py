@@ -543,7 +543,7 @@ def test_cost_volume_backward_vs_autograd(ops, shape, d4):
   assert (tc.grad.cpu().double() - to.grad).abs().max().item() <= 1e-5 * max(1.0, to.grad.abs().max().item())
 
 
-@pytest.mark.parametrize('B,d4,h4,w4', [(2, 4, 16, 8), (1, 8, 8, 16), (1, 16, 12, 100), (2, 48, 8, 4)])
+@pytest.mark.parametrize('B,d4,h4,w4', [(2, 4, 16, 8), (1, 8, 8, 16), (1, 16, 12, 100), (2, 48, 8, 4), (1, 48, 4, 64), (2, 48, 7, 128)])
 def test_disp_regress_backward_vs_autograd(ops, B, d4, h4, w4):
   """Fused soft-argmin head backward against autograd through F.interpolate + softmax + weighted sum (fp64 on CPU)."""
   g = torch.Generator().manual_seed(d4 + w4)
@@ -559,6 +559,9 @@ def test_disp_regress_backward_vs_autograd(ops, B, d4, h4, w4):
   err = (cc.grad.cpu().double() - co.grad).abs().max().item()
   assert err <= 2e-5 * max(1.0, co.grad.abs().max().item()), err
   assert (pred.detach().cpu() - O.disparity_regression(cost, D, H, W)).abs().max().item() <= 1e-4 * D
+  if d4 == 48 and W % 256 == 0:  # two-pass workspace path (gather transpose): bit-identical from run to run
+    g2 = ops.disp_regress_backward(cost[:, 0].cuda().contiguous(), gp.cuda(), D)
+    assert torch.equal(g2, cc.grad[:, 0]) and torch.equal(ops.disp_regress_backward(cost[:, 0].cuda().contiguous(), gp.cuda(), D), g2)
 
 
 def test_registered_ops_pass_opcheck(ops):
