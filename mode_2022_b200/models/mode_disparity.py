@@ -153,8 +153,11 @@ class ModeDisparity(nn.Module):
     to end in fp32.  libmode_b200 forward AND backward kernels: the spherical layers (SphereConvFunction, SURVEY.md section 8
     a3), the cost volume and the three soft-argmin heads; the conv2d / conv3d / BatchNorm layers are the library code the
     reference trains with (cuDNN through autograd)."""
-    fl = self.feature_extraction(left.float())
-    fr = self.feature_extraction(right.float())
+    left, right = left.float(), right.float()
+    if self.train_channels_last:  # the regular 2-D layers run NHWC end to end (cuDNN's native layout); the spherical layers convert back
+      left, right = left.contiguous(memory_format=torch.channels_last), right.contiguous(memory_format=torch.channels_last)
+    fl = self.feature_extraction(left)
+    fr = self.feature_extraction(right)
     d4 = self.maxdisp // 4
     # integer shifts: cost[:, :C, i, :, i:] = ref[..., i:], cost[:, C:, i, :, i:] = tgt[..., :W-i] -- one kernel; its backward is a
     # deterministic gather-sum over the shifts (mode_cost_volume_backward_f32), registered on the op with torch.library

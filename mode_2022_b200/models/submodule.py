@@ -117,5 +117,10 @@ class sphere_feature_extraction(nn.Module):
     """Training path (reference submodule.py:192-201): plain module execution, differentiable end to end."""
     raw = self.layer2(self.layer1(self.firstconv(x)))
     reg = self.layer3(raw)
-    sph = self.layer4(reg)
+    # the spherical layers read and write NCHW (the reference op's layout): when the regular layers run channels-last (training,
+    # mode_disparity.py) convert ONCE here instead of once per spherical conv and residual add, and come back for lastconv
+    cl = reg.dim() == 4 and not reg.is_contiguous() and reg.is_contiguous(memory_format=torch.channels_last)
+    sph = self.layer4(reg.contiguous() if cl else reg)
+    if cl:
+      sph = sph.contiguous(memory_format=torch.channels_last)
     return self.lastconv(torch.cat((raw, reg, sph), 1))
