@@ -530,7 +530,7 @@ def run_train(args):
         'config': {'workload': f'ModeDisparity training step (3 heads, smooth-L1, Adam), global batch {gb} pairs, Cassini 1024x512, maxdisp=192', 'pairs_per_gpu': nb,
                    'parallelism': f'camera pairs sharded over {world} GPU(s); bucketed NCCL gradient all-reduce ({reducer.grad_bytes() / 1e6:.1f} MB in {len(reducer.buckets)} buckets) '
                                   'launched from autograd hooks, overlapped with the backward pass',
-                   'custom_kernels': 'sphere conv fwd+bwd, cost volume fwd+bwd, soft-argmin heads fwd+bwd (libmode_b200); conv2d/conv3d/BN: cuDNN'},
+                   'custom_kernels': 'sphere conv fwd+bwd, cost volume fwd+bwd, soft-argmin heads fwd+bwd, BatchNorm2d/3d fwd+bwd (libmode_b200); conv2d/conv3d: cuDNN TF32 on channels-last tensors'},
         'e2e': {'value': round(gb * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'pairs/s', 'h2d_bytes_per_step': int(nb * (2 * 3 + 1) * H * W * 4 + nb * H * W),
                 'd2h_bytes_per_step': 4, 'ms_per_step': round(ms_e2e / args.steps, 2)},
         'gpu_launches': int(launches), 'clocks': clocks, 'loss': float(loss_box[0]),
