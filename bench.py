@@ -482,6 +482,7 @@ def run_train(args):
   if gb % world:
     raise SystemExit(f'--mode train: global batch {gb} is not divisible by {world} ranks')
   nb = gb // world
+  torch.backends.cudnn.benchmark = True  # as the reference's training script (train_disparity.py:82: benchmark = not args.cudnn_deter)
   torch.manual_seed(0)
   model = ModeDisparity(MAXDISP, conv='Sphere', in_height=H, in_width=W, sphereType='Cassini', precision='fp32').to(dev).train()
   reducer = T.GradAllReduce(model.parameters())

@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mode_2022_b200.models import ModeDisparity
 from mode_2022_b200 import training as T
 H, W, D, B = 1024, 512, 192, int(os.environ.get('BATCH', 1))
+torch.backends.cudnn.benchmark = os.environ.get('CUDNN_BENCHMARK', '1') != '0'  # the reference trains with cudnn.benchmark on (train_disparity.py:82)
 torch.manual_seed(0)
 m = ModeDisparity(D, in_height=H, in_width=W, sphereType='Cassini', precision='fp32').cuda().train()
 red = T.GradAllReduce(m.parameters())
@@ -13,7 +14,7 @@ g = torch.Generator().manual_seed(1)
 left, right = torch.randn(B, 3, H, W, generator=g).cuda(), torch.randn(B, 3, H, W, generator=g).cuda()
 disp = (torch.rand(B, 1, H, W, generator=g) * (D - 1)).cuda()
 mask = (torch.rand(B, 1, H, W, generator=g) < 0.9).cuda()
-for _ in range(2):
+for _ in range(3):
   T.train_step(m, red, opt, left, right, disp, mask)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
